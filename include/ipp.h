@@ -1,0 +1,167 @@
+/* ipp.h -- C ABI of libipp.so, the B200-native plan-fitness evaluator.
+ *
+ * Drop-in boundary for the SWIG-exposed evaluator of kaiolae/Inspection-Path-Planning
+ * (plan_optimizer/cpp_wrapper/cpp_binding.i:1-40).  Every entry point names the
+ * reference interface it replaces.  Plain C types only: pointers, sizes, ints,
+ * doubles.  All functions returning int return 0 on success and non-zero on
+ * error; the message is available from ipp_last_error() (thread local).
+ *
+ * There is no CPU fallback: every compute call needs a CUDA device (sm_100a).
+ *
+ * Conventions
+ *   - a "plan" is a sequence of genes; a gene is [boxId] (width 1) or
+ *     [boxId, angleOffsetRad] (width 2), exactly as in the reference
+ *     (plan_evaluator/Evaluator/src/PlanInterpreterBoxOrder.cpp:278-299).
+ *   - populations travel in CSR form: `ids` (int32, one per gene), optional
+ *     `angles` (float, one per gene, NULL = width-1 genes) and `offsets`
+ *     (int64, pop+1 entries).
+ *   - fitness rows are 4 doubles: {coverageScore, energy, pathLength,
+ *     collidingEdges}.  Columns 0-1 are the reference's evaluatePlan() pair
+ *     (PlanCoverageEstimator.cpp:201-282); columns 2-3 are extra.
+ *   - seen-triangle bitmaps are uint32 words, bit (id & 31) of word (id >> 5),
+ *     id = triangle index in mesh file order (the reference's colour ID,
+ *     Utility_Functions/src/TriangleData.cpp:23-39).
+ */
+#ifndef IPP_H_
+#define IPP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipp_evaluator ipp_t;
+
+/* plotting_style enum, cpp_binding.i:20 */
+enum { IPP_PLOT_NORMAL = 0, IPP_PLOT_CIRCULATING = 1, IPP_PLOT_IMAGE = 2, IPP_PLOT_NOTHING = 3 };
+
+const char* ipp_last_error(void);
+/* number of CUDA devices visible (0 if none / no driver) */
+int ipp_device_count(void);
+
+/* PlanCoverageEstimator::PlanCoverageEstimator  (cpp_binding.i:29,
+ * PlanCoverageEstimator.cpp:167-195).  sensor_specs[8] = {sampleInterval, fov_x,
+ * fov_y, imageHeight, zNear, zFar, frontCam, downCam} (CameraEstimator.h:83-92).
+ * start_xyz may be NULL; it is copied (the reference borrows the pointer).
+ * device = CUDA ordinal.  Loads .stl / .obj (and the flat .ippm test format),
+ * builds the BVH, the candidate-viewpoint grid, the circling seed plans and the
+ * energy limit. */
+int ipp_create(const char* scene_path, const double* sensor_specs, int post_processing, const double* start_xyz,
+               int plan_loops_around, int printer_friendly, int device, ipp_t** out);
+/* ~PlanCoverageEstimator */
+void ipp_destroy(ipp_t* h);
+
+/* getNumberOfBoxes (cpp_binding.i:32) */
+int ipp_num_boxes(const ipp_t* h);
+/* SceneKeeper::getTriangleCount */
+int64_t ipp_num_triangles(const ipp_t* h);
+/* words per seen-triangle bitmap = ceil(T/32) */
+int64_t ipp_bitmap_words(const ipp_t* h);
+/* getMaxAllowedEnergy (cpp_binding.i:36); -1 when post_processing */
+double ipp_max_allowed_energy(const ipp_t* h);
+/* scene constants derived at load (SceneKeeper.cpp:65-71, TriangleData.cpp:65-72) */
+double ipp_total_area(const ipp_t* h);
+double ipp_collision_penalty(const ipp_t* h);
+void ipp_scene_info(const ipp_t* h, double* center3, double* bbox6);
+void ipp_image_size(const ipp_t* h, int* width, int* height);
+/* per-triangle Heron areas, file order (TriangleData.cpp:56-61) */
+int ipp_areas(const ipp_t* h, double* out_T);
+/* candidate viewpoint centres, N x 3 (PlanInterpreterBoxOrder::divideIntoBoxes :193-251) */
+int ipp_box_centres(const ipp_t* h, double* out_Nx3);
+/* boxVolume[z][x][y] classification grid: -1 too close, -2 nothing visible, else box id */
+void ipp_grid_dims(const ipp_t* h, int* nz, int* nx, int* ny);
+int ipp_grid(const ipp_t* h, int32_t* out);
+
+/* getSimplePlans (cpp_binding.i:34; PlanInterpreterBoxOrder.cpp:111-160) in CSR form.
+ * Call with ids == NULL to obtain the sizes. */
+int ipp_simple_plans(ipp_t* h, int* n_plans, int* n_genes, double* ids, int32_t* offsets);
+
+/* evaluatePlan (cpp_binding.i:31).  genes: n x width doubles.  how_to_plot must
+ * be IPP_PLOT_NOTHING (the GL viewers are out of scope).  out4 receives one
+ * fitness row. */
+int ipp_evaluate_plan(ipp_t* h, const double* genes, int n, int width, int memoization, int how_to_plot,
+                      int disable_energy_limit, double* out4);
+
+/* The one batched entry point: evaluatePlan over a whole population
+ * (replaces toolbox.map(evaluate, ...) at plan_optimizer/optimize_coverage.py:141,191).
+ * Host pointers; copies in and out are part of the call.  union_bitmap may be
+ * NULL; otherwise it receives the OR of the seen sets of all plans that passed
+ * the energy gate (W words). */
+int ipp_evaluate_population(ipp_t* h, const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop,
+                            int memoization, int disable_energy_limit, double* fitness_popx4, uint32_t* union_bitmap);
+
+/* Same computation with every buffer already resident in device memory
+ * (d_* are CUDA device pointers obtained from ipp_device_alloc).  Asynchronous
+ * on the evaluator's stream; call ipp_sync() before reading results. */
+int ipp_evaluate_population_device(ipp_t* h, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets,
+                                   int64_t pop, int64_t n_genes, int memoization, int disable_energy_limit,
+                                   double* d_fitness_popx4);
+
+/* updateMemoisedEdges (cpp_binding.i:33; PlanCoverageEstimator.cpp:284-327):
+ * drop every cached edge bitmap whose key is not in the population; returns the
+ * surviving count in *remaining. */
+int ipp_update_memoised_edges(ipp_t* h, const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop,
+                              int64_t* remaining);
+/* number of edge bitmaps currently memoised */
+int64_t ipp_memo_size(const ipp_t* h);
+/* drop all memoised edges and collision flags */
+int ipp_clear_memo(ipp_t* h);
+
+/* interpretAndExportPlan (cpp_binding.i:38; PlanInterpreterBoxOrder.cpp:301-324).
+ * pos: up to (n+1) x 3, dirs: up to (n+1) x 3. */
+int ipp_interpret_plan(const ipp_t* h, const double* genes, int n, int width, double* pos, double* dirs, int* n_pos,
+                       int* n_dirs);
+
+/* ---- test hooks for per-kernel parity ---- */
+/* seen-triangle bitmap of one plan edge prev->curr (prev = -1: the start location),
+ * GetColorsDuringTraversal (CameraEstimator.cpp:131-178). */
+int ipp_edge_bitmap(ipp_t* h, int prev, int curr, double angle, uint32_t* out_W);
+/* edgeComesTooCloseToStructure (OsgHelpers.cpp:246-262) for n edges given as xyz pairs (n x 6 doubles) */
+int ipp_edges_collide(ipp_t* h, const double* edges_nx6, int64_t n, uint8_t* out_flags);
+/* checkPolytopeForIntersections(generateBoxPolytope(c, half)) (OsgHelpers.cpp:295-332) for n cubes (n x 3) */
+int ipp_boxes_hit_mesh(ipp_t* h, const double* centres_nx3, int64_t n, double half_side, uint8_t* out_flags);
+/* one camera pose -> per-pixel nearest triangle id (-1 background), row-major [y][x] */
+int ipp_render_ids(ipp_t* h, const double* eye3, const double* center3, const double* up3, int32_t* out_HxW);
+/* BVH self-check: closest-hit of n rays (origin xyz, dir xyz) through the BVH and by brute force; returns
+ * the number of mismatching ids */
+int ipp_bvh_selftest(ipp_t* h, const float* rays_nx6, int64_t n, int32_t* out_ids, int64_t* mismatches);
+
+/* ---- device memory, stream, timing (plumbing for bench.py) ---- */
+int ipp_device_alloc(ipp_t* h, int64_t bytes, void** out);
+int ipp_device_free(ipp_t* h, void* p);
+int ipp_host_alloc(int64_t bytes, void** out); /* pinned */
+int ipp_host_free(void* p);
+int ipp_memcpy_h2d(ipp_t* h, void* dst, const void* src, int64_t bytes);
+int ipp_memcpy_d2h(ipp_t* h, void* dst, const void* src, int64_t bytes);
+int ipp_sync(ipp_t* h);
+/* CUDA events on the evaluator's stream */
+int ipp_timer_start(ipp_t* h);
+int ipp_timer_stop(ipp_t* h, double* ms);
+/* overwrite a buffer larger than L2 */
+int ipp_flush_l2(ipp_t* h);
+/* counters since the last reset: [0] kernel launches, [1] pixel-centre rays issued, [2] snapshots rendered,
+ * [3] edges rendered, [4] collision queries, [5] plan_reduce launches, [6] plans reduced, [7] bitmap rows read */
+int ipp_counters(ipp_t* h, int64_t* out8, int reset);
+/* accumulated CUDA-event time of a named kernel group since the last reset:
+ * 0 = plan_reduce, 1 = edge_visibility, 2 = edge_collision, 3 = pack, 4 = energy+mark */
+int ipp_kernel_time(ipp_t* h, int which, double* ms, int64_t* launches, int reset);
+int ipp_set_profiling(ipp_t* h, int on);
+
+/* ---- multi-GPU: one process per GPU, population sharded by individual ---- */
+/* 128-byte NCCL unique id (rank 0 creates, the host side distributes it) */
+int ipp_comm_unique_id(uint8_t* out128);
+int ipp_comm_init(ipp_t* h, int rank, int world, const uint8_t* id128);
+int ipp_comm_destroy(ipp_t* h);
+/* evaluate this rank's contiguous shard of the population and all-gather the
+ * fitness rows (one ncclAllGather over NVLink) so every rank holds all pop x 4. */
+int ipp_evaluate_population_sharded(ipp_t* h, const int32_t* ids, const float* angles, const int64_t* offsets,
+                                    int64_t pop, int memoization, int disable_energy_limit, double* fitness_popx4);
+int ipp_comm_barrier(ipp_t* h);
+int ipp_comm_allreduce_max(ipp_t* h, double* inout, int n);
+int ipp_comm_allreduce_sum(ipp_t* h, double* inout, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPP_H_ */

@@ -1,0 +1,272 @@
+"""Drop-in for the reference's SWIG module `cpp_wrapper.cpp_binding`
+(plan_optimizer/cpp_wrapper/cpp_binding.i:1-40, cpp_binding.py:512-549): same module-level names, same
+class, same method names, argument order and return shapes -- backed by libipp.so on a B200.
+
+    from inspection_path_planning_b200 import cpp_binding
+    ev = cpp_binding.PlanCoverageEstimator(scene, [2.0, 46, 46, 1024, 0.1, 10, 1, 1])
+    coverage, energy = ev.evaluatePlan([[3], [17], [4]], True, cpp_binding.nothing)
+    fitness = ev.evaluatePopulation(list_of_plans, True)      # the one batched entry point
+
+Differences from the SWIG build, all deliberate:
+  * startLocation is copied (the reference keeps a borrowed pointer to a `Line`); any sequence of 3 numbers works.
+  * C++ exceptions become Python exceptions instead of terminating the interpreter (the reference has no %exception).
+  * the GL viewers (how_to_plot != nothing, storePlanImage, viewMatrixSelector) are out of scope and raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+# enum plotting_style, cpp_binding.i:20
+normal, circulating, image, nothing = 0, 1, 2, 3
+
+
+class Line(list):
+    """std::vector<double> stand-in (cpp_binding.i:13)."""
+
+
+class Array(list):
+    """std::vector<std::vector<double>> stand-in (cpp_binding.i:14)."""
+
+
+class StringVector(list):
+    """std::vector<std::string> stand-in (cpp_binding.i:16)."""
+
+
+def viewMatrixSelector(sceneFileName):
+    """cpp_binding.i:23 -- opens an interactive OSG viewer in the reference; out of scope here."""
+    raise NotImplementedError("viewMatrixSelector needs an interactive OpenGL viewer; not part of the B200 evaluator")
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.c_f64p)
+
+
+def pack_population(plans):
+    """list of plans -> (ids int32[nGenes], offsets int64[pop+1]).  Each gene is [id] (or a bare id).
+    Gene -> id uses the reference's rounding `(size_t)(gene + 0.5)` (PlanInterpreterBoxOrder.cpp:280)."""
+    offsets = np.zeros(len(plans) + 1, dtype=np.int64)
+    flat = []
+    for i, p in enumerate(plans):
+        for g in p:
+            if isinstance(g, (list, tuple, np.ndarray)):
+                if len(g) != 1:
+                    raise NotImplementedError("[id, angle] genes are not supported by the batched path yet")
+                g = g[0]
+            flat.append(g)
+        offsets[i + 1] = len(flat)
+    vals = np.asarray(flat, dtype=np.float64)
+    ids = np.trunc(vals + 0.5)
+    ids[vals + 0.5 < 0] = 0.0  # a negative gene (the -1 cells of the seed plans) truncates to 0 like the reference
+    return np.ascontiguousarray(ids.astype(np.int32)), offsets
+
+
+class PlanCoverageEstimator(object):
+    """PlanCoverageEstimator (cpp_binding.i:25-39; PlanCoverageEstimator.h:51-165)."""
+
+    def __init__(self, sceneFileName, sensorSpecs, postProcessing=False, startLocation=None, planLoopsAround=False,
+                 printerFriendly=True, device=None):
+        L = _lib.load()
+        if L.ipp_device_count() < 1:
+            raise RuntimeError("no CUDA device visible: the B200 evaluator has no CPU fallback")
+        specs = np.ascontiguousarray(list(sensorSpecs), dtype=np.float64)
+        if specs.size != 8:
+            raise ValueError("sensorSpecs needs 8 values: [sampleInterval, fov_x, fov_y, imageHeight, zNear, zFar, front, down]")
+        start = None
+        if startLocation is not None:
+            start = np.ascontiguousarray(list(startLocation), dtype=np.float64)
+            if start.size != 3:
+                raise ValueError("startLocation needs 3 values")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) % max(1, L.ipp_device_count())
+        h = _lib.H()
+        _lib.check(L.ipp_create(os.fsencode(sceneFileName), _dp(specs), int(bool(postProcessing)), None if start is None else _dp(start),
+                                int(bool(planLoopsAround)), int(bool(printerFriendly)), int(device), C.byref(h)))
+        self._L = L
+        self._h = h
+        self.device = device
+        self.T = int(L.ipp_num_triangles(h))
+        self.W32 = int(L.ipp_bitmap_words(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ipp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the reference's methods ----
+    def evaluatePlan(self, plan, memoization, how_to_plot, disableEnergyLimit=False):
+        """-> (coverageScore, energy); cpp_binding.i:31."""
+        genes = np.zeros((len(plan), 1), dtype=np.float64)
+        for i, g in enumerate(plan):
+            if isinstance(g, (list, tuple, np.ndarray)):
+                if len(g) != 1:
+                    raise NotImplementedError("[id, angle] genes are not supported by the batched path yet")
+                g = g[0]
+            genes[i, 0] = g
+        out = np.zeros(4, dtype=np.float64)
+        _lib.check(self._L.ipp_evaluate_plan(self._h, _dp(genes), genes.shape[0], 1, int(bool(memoization)), int(how_to_plot),
+                                             int(bool(disableEnergyLimit)), _dp(out)))
+        return (float(out[0]), float(out[1]))
+
+    def getNumberOfBoxes(self):
+        return int(self._L.ipp_num_boxes(self._h))
+
+    def updateMemoisedEdges(self, allSolutions):
+        ids, offsets = allSolutions if isinstance(allSolutions, tuple) else pack_population(allSolutions)
+        rem = C.c_int64()
+        _lib.check(self._L.ipp_update_memoised_edges(self._h, ids.ctypes.data_as(_lib.c_i32p), None, offsets.ctypes.data_as(_lib.c_i64p),
+                                                     offsets.size - 1, C.byref(rem)))
+        return int(rem.value)
+
+    def getSimplePlans(self):
+        n, g = C.c_int(), C.c_int()
+        _lib.check(self._L.ipp_simple_plans(self._h, C.byref(n), C.byref(g), None, None))
+        ids = np.zeros(max(g.value, 1), dtype=np.float64)
+        off = np.zeros(n.value + 1, dtype=np.int32)
+        _lib.check(self._L.ipp_simple_plans(self._h, C.byref(n), C.byref(g), _dp(ids), off.ctypes.data_as(_lib.c_i32p)))
+        return tuple(tuple((float(ids[k]),) for k in range(off[i], off[i + 1])) for i in range(n.value))
+
+    def storePlanImage(self, plan, viewMatrix, storagePath):
+        raise NotImplementedError("storePlanImage renders through an OpenGL viewer; not part of the B200 evaluator")
+
+    def getMaxAllowedEnergy(self):
+        return float(self._L.ipp_max_allowed_energy(self._h))
+
+    def interpretAndExportPlan(self, plan, arg3=None, arg4=None):
+        """-> [positions, headings]; cpp_binding.i:38 (SWIG INOUT typemap)."""
+        width = 1
+        for g in plan:
+            if isinstance(g, (list, tuple, np.ndarray)):
+                width = max(width, len(g))
+        genes = np.zeros((len(plan), width), dtype=np.float64)
+        for i, g in enumerate(plan):
+            if isinstance(g, (list, tuple, np.ndarray)):
+                genes[i, :len(g)] = g
+            else:
+                genes[i, 0] = g
+        n = genes.shape[0]
+        pos = np.zeros((n + 1, 3))
+        dirs = np.zeros((n + 1, 3))
+        npos, ndir = C.c_int(), C.c_int()
+        _lib.check(self._L.ipp_interpret_plan(self._h, _dp(genes), n, width, _dp(pos), _dp(dirs), C.byref(npos), C.byref(ndir)))
+        return [pos[:npos.value].tolist(), dirs[:ndir.value].tolist()]
+
+    # ---- the batched entry point ----
+    def evaluatePopulation(self, plans, memoization=True, disableEnergyLimit=False, union_bitmap=False, out=None):
+        """Evaluates a whole population in one call.  `plans` is a list of plans or a packed (ids int32, offsets int64)
+        pair.  Returns float64 [pop, 4]: columns 0-1 are evaluatePlan's (coverageScore, energy), 2 = path length,
+        3 = number of colliding edges.  With union_bitmap=True also returns the OR of the seen sets (uint32 words)."""
+        ids, offsets = plans if isinstance(plans, tuple) else pack_population(plans)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        pop = offsets.size - 1
+        fit = out if out is not None else np.empty((pop, 4), dtype=np.float64)
+        ub = np.zeros(self.W32, dtype=np.uint32) if union_bitmap else None
+        _lib.check(self._L.ipp_evaluate_population(self._h, ids.ctypes.data_as(_lib.c_i32p), None, offsets.ctypes.data_as(_lib.c_i64p), pop,
+                                                   int(bool(memoization)), int(bool(disableEnergyLimit)), _dp(fit),
+                                                   None if ub is None else ub.ctypes.data_as(_lib.c_u32p)))
+        return (fit, ub) if union_bitmap else fit
+
+    def evaluatePopulationSharded(self, plans, memoization=True, disableEnergyLimit=False, out=None):
+        """Multi-GPU form (after comm_init): this rank evaluates its contiguous shard, one NCCL all-gather returns every
+        plan's fitness row to every rank."""
+        ids, offsets = plans if isinstance(plans, tuple) else pack_population(plans)
+        pop = offsets.size - 1
+        fit = out if out is not None else np.empty((pop, 4), dtype=np.float64)
+        _lib.check(self._L.ipp_evaluate_population_sharded(self._h, ids.ctypes.data_as(_lib.c_i32p), None, offsets.ctypes.data_as(_lib.c_i64p),
+                                                           pop, int(bool(memoization)), int(bool(disableEnergyLimit)), _dp(fit)))
+        return fit
+
+    # ---- scene facts and test hooks ----
+    def memo_size(self):
+        return int(self._L.ipp_memo_size(self._h))
+
+    def clear_memo(self):
+        _lib.check(self._L.ipp_clear_memo(self._h))
+
+    def total_area(self):
+        return float(self._L.ipp_total_area(self._h))
+
+    def collision_penalty(self):
+        return float(self._L.ipp_collision_penalty(self._h))
+
+    def scene_info(self):
+        c, b = np.zeros(3), np.zeros(6)
+        self._L.ipp_scene_info(self._h, _dp(c), _dp(b))
+        return c, b
+
+    def image_size(self):
+        w, h = C.c_int(), C.c_int()
+        self._L.ipp_image_size(self._h, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def areas(self):
+        a = np.zeros(self.T)
+        _lib.check(self._L.ipp_areas(self._h, _dp(a)))
+        return a
+
+    def box_centres(self):
+        out = np.zeros((self.getNumberOfBoxes(), 3))
+        _lib.check(self._L.ipp_box_centres(self._h, _dp(out)))
+        return out
+
+    def grid(self):
+        nz, nx, ny = C.c_int(), C.c_int(), C.c_int()
+        self._L.ipp_grid_dims(self._h, C.byref(nz), C.byref(nx), C.byref(ny))
+        g = np.zeros((nz.value, nx.value, ny.value), dtype=np.int32)
+        _lib.check(self._L.ipp_grid(self._h, g.ctypes.data_as(_lib.c_i32p)))
+        return g
+
+    def edge_bitmap(self, prev, curr, angle=0.0):
+        out = np.zeros(self.W32, dtype=np.uint32)
+        _lib.check(self._L.ipp_edge_bitmap(self._h, int(prev), int(curr), float(angle), out.ctypes.data_as(_lib.c_u32p)))
+        return out
+
+    def edges_collide(self, edges):
+        e = np.ascontiguousarray(edges, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(e.shape[0], dtype=np.uint8)
+        _lib.check(self._L.ipp_edges_collide(self._h, _dp(e), e.shape[0], out.ctypes.data_as(_lib.c_u8p)))
+        return out.astype(bool)
+
+    def boxes_hit_mesh(self, centres, half_side):
+        c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(c.shape[0], dtype=np.uint8)
+        _lib.check(self._L.ipp_boxes_hit_mesh(self._h, _dp(c), c.shape[0], float(half_side), out.ctypes.data_as(_lib.c_u8p)))
+        return out.astype(bool)
+
+    def render_ids(self, eye, center, up):
+        w, h = self.image_size()
+        out = np.zeros((h, w), dtype=np.int32)
+        e, c, u = (np.ascontiguousarray(x, dtype=np.float64) for x in (eye, center, up))
+        _lib.check(self._L.ipp_render_ids(self._h, _dp(e), _dp(c), _dp(u), out.ctypes.data_as(_lib.c_i32p)))
+        return out
+
+    def bvh_selftest(self, rays):
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        ids = np.zeros(r.shape[0], dtype=np.int32)
+        mism = C.c_int64()
+        _lib.check(self._L.ipp_bvh_selftest(self._h, r.ctypes.data_as(_lib.c_f32p), r.shape[0], ids.ctypes.data_as(_lib.c_i32p), C.byref(mism)))
+        return ids, int(mism.value)
+
+    # ---- plumbing used by bench.py ----
+    def sync(self):
+        _lib.check(self._L.ipp_sync(self._h))
+
+    def counters(self, reset=False):
+        out = np.zeros(8, dtype=np.int64)
+        _lib.check(self._L.ipp_counters(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
+        keys = ["launches", "rays", "snapshots", "edges_rendered", "collision_queries", "reduce_launches", "plans_reduced", "rows_read"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def kernel_time(self, which, reset=False):
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self._L.ipp_kernel_time(self._h, int(which), C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, int(n.value)

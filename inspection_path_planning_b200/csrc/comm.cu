@@ -1,0 +1,139 @@
+// comm.cu -- see comm.h.  NCCL is loaded with dlopen so that libipp.so has no link-time dependency on it;
+// the population is sharded by individual, the mesh and BVH are replicated per GPU, and the only exchange
+// step is one ncclAllGather of the fitness rows per generation.  plan_reduce writes each
+// rank's rows straight into its slot of the gather buffer (in-place all-gather, no staging copy).
+#include "comm.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "evaluator.h"
+
+namespace ipp {
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& api() {
+    static NcclApi a;
+    if (!a.lib) {
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) throw std::runtime_error(std::string("libipp: cannot load NCCL: ") + dlerror());
+        auto sym = [&](const char* n) {
+            void* p = dlsym(a.lib, n);
+            if (!p) throw std::runtime_error(std::string("libipp: NCCL symbol missing: ") + n);
+            return p;
+        };
+        a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+        a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+        a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+        a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    }
+    return a;
+}
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) throw std::runtime_error(std::string("libipp: NCCL error in ") + what + ": " + api().GetErrorString(r));
+}
+}  // namespace
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    double* d_small = nullptr;  // all-reduce scratch
+    double* d_gather = nullptr; // world * per * 4 fitness doubles
+    int64_t gatherCap = 0;
+    int32_t* d_ids = nullptr;
+    int64_t* d_offsets = nullptr;
+    int64_t idsCap = 0, offCap = 0;
+};
+
+void comm_unique_id(uint8_t out128[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    nccl_check(api().GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(out128, &id, 128);
+}
+
+Comm* comm_create(int rank, int world, const uint8_t id128[128], cudaStream_t st) {
+    (void)st;
+    Comm* c = new Comm;
+    c->rank = rank;
+    c->world = world;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    nccl_check(api().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
+    IPP_CUDA_CHECK(cudaMalloc(&c->d_small, 64 * sizeof(double)));
+    return c;
+}
+void comm_destroy(Comm* c) {
+    if (!c) return;
+    if (c->comm) api().CommDestroy(c->comm);
+    cudaFree(c->d_small);
+    cudaFree(c->d_gather);
+    cudaFree(c->d_ids);
+    cudaFree(c->d_offsets);
+    delete c;
+}
+int comm_rank(const Comm* c) { return c->rank; }
+int comm_world(const Comm* c) { return c->world; }
+
+void comm_allreduce(Comm* c, double* inout, int n, int op, cudaStream_t st) {
+    if (n > 64) throw std::invalid_argument("libipp: all-reduce of at most 64 doubles");
+    IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_small, inout, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    nccl_check(api().AllReduce(c->d_small, c->d_small, (size_t)n, ncclDouble, op == 1 ? ncclMax : ncclSum, c->comm, st), "ncclAllReduce");
+    IPP_CUDA_CHECK(cudaMemcpyAsync(inout, c->d_small, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    IPP_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, int64_t per,
+                             int64_t lo, int64_t hi, bool memo, bool noLimit, double* fitness) {
+    Comm* c = ev.comm_;
+    cudaStream_t st = ev.stream();
+    if (angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
+    const int64_t mine = hi - lo;
+    const int64_t g0 = offsets[lo], nGenes = offsets[hi] - g0;
+    if (c->world * per * 4 > c->gatherCap) {
+        cudaFree(c->d_gather);
+        c->gatherCap = c->world * per * 4 + 1024;
+        IPP_CUDA_CHECK(cudaMalloc(&c->d_gather, (size_t)c->gatherCap * sizeof(double)));
+    }
+    if (nGenes + 1 > c->idsCap) {
+        cudaFree(c->d_ids);
+        c->idsCap = nGenes + nGenes / 4 + 16;
+        IPP_CUDA_CHECK(cudaMalloc(&c->d_ids, (size_t)c->idsCap * sizeof(int32_t)));
+    }
+    if (mine + 2 > c->offCap) {
+        cudaFree(c->d_offsets);
+        c->offCap = mine + mine / 4 + 16;
+        IPP_CUDA_CHECK(cudaMalloc(&c->d_offsets, (size_t)c->offCap * sizeof(int64_t)));
+    }
+    std::vector<int64_t> off((size_t)mine + 1);
+    for (int64_t i = 0; i <= mine; ++i) off[i] = offsets[lo + i] - g0;
+    double* d_mine = c->d_gather + (size_t)c->rank * per * 4;
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_mine, 0, (size_t)per * 4 * sizeof(double), st));
+    if (mine > 0) {
+        IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_ids, ids + g0, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_offsets, off.data(), (size_t)(mine + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        ev.evaluatePopulationDevice(c->d_ids, nullptr, c->d_offsets, mine, nGenes, memo, noLimit, d_mine, nullptr);
+    }
+    // the one exchange step: every rank receives every shard's fitness rows over NVLink
+    nccl_check(api().AllGather(d_mine, c->d_gather, (size_t)per * 4, ncclDouble, c->comm, st), "ncclAllGather");
+    IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, c->d_gather, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    IPP_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+}  // namespace ipp

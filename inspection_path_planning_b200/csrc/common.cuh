@@ -1,0 +1,73 @@
+// common.cuh -- shared declarations of the libipp.so translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#define IPP_CUDA_CHECK(expr)                                                                            \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " +   \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");       \
+    } while (0)
+
+namespace ipp {
+
+// Compiled-in constants of the reference: Utility_Functions/src/Constants.h:19-60
+constexpr double kNumViewpointsInsideVolume = 1000.0;
+constexpr double kBoxSafetyMargin = 2.0;
+constexpr double kBoxPadding = 4.0;
+constexpr double kMinDistFromBottom = 3.0;
+constexpr bool kDownwardCameraActive = true;
+constexpr double kTranslationEnergyFactor = 0.1;
+constexpr double kRotationEnergyFactor = 1.0;
+constexpr double kMaxEnergyMultiplier = 1.0;
+constexpr double kCollisionPenaltyModifier = 2.0;
+constexpr double kEdgeSafetyBuffer = 1.5;
+constexpr double kCameraFarPlaneDist = 10.0;
+
+constexpr int kLeafMax = 4;          // triangles per BVH leaf
+constexpr int kTileWords = 128;      // bitmap words per plan_reduce tile (one uint4 per lane)
+constexpr int kTileTris = kTileWords * 32;
+
+// One 64-byte BVH node: the boxes of both children and their links.
+//   q0 = (c0min.x, c0min.y, c0min.z, c0max.x)  q1 = (c0max.y, c0max.z, c1min.x, c1min.y)
+//   q2 = (c1min.z, c1max.x, c1max.y, c1max.z)  q3 = (link0, link1, -, -) as int bits
+// link >= 0: internal node index; link < 0: leaf, ~link = (first << 3) | count, count in 0..kLeafMax
+struct BvhNode {
+    float4 q0, q1, q2, q3;
+};
+
+struct DeviceScene {
+    int T = 0;        // triangles
+    int Tpad = 0;     // T rounded up to 32
+    int nNodes = 0;   // BVH nodes (root = 0)
+    // BVH-ordered triangles, canonical (lexicographic) vertex order; a.w = original id as int bits
+    float4 *ta = nullptr, *tb = nullptr, *tc = nullptr;
+    // BVH-ordered triangles, file vertex order (exact collision predicate); a.w = original id
+    float4 *oa = nullptr, *ob = nullptr, *oc = nullptr;
+    BvhNode* nodes = nullptr;
+    double* area = nullptr;   // [areaPad] file order, zero padded to a multiple of kTileTris
+    float bbmin[3], bbmax[3]; // float bounding box of all vertices
+};
+
+// Per-camera-pose record consumed by the visibility kernel
+struct Snapshot {
+    double f[3], s[3], u[3];  // look-at basis (world space)
+    float eye[3];
+    int slot;                 // flag row within the current batch
+    int rx0, ry0, rnx, rny;   // rectangle of 32x32 macro tiles that may see the scene
+};
+
+struct CameraParams {
+    double tanX, tanY;
+    float zNear, zFar;
+    int W, H;
+    bool front, down;
+    double sampleInterval;
+};
+
+}  // namespace ipp

@@ -1,0 +1,645 @@
+// evaluator.cu -- host orchestration of the CUDA plan evaluator (see evaluator.h).
+// Flow of one population (PlanCoverageEstimator::evaluatePlan, PlanCoverageEstimator.cpp:201-282, batched):
+//   mark unknown collision flags -> K5 -> energy + gate -> mark unknown edge bitmaps of gated-in plans
+//   -> K3 decode -> K4 visibility -> pack -> K6 plan_reduce.
+#include "evaluator.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "exact.cuh"
+#include "kernels.h"
+#include "mesh_io.h"
+
+namespace ipp {
+
+namespace {
+template <class T>
+T* dalloc(size_t n) {
+    T* p = nullptr;
+    IPP_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+}  // namespace
+
+Evaluator::Evaluator(const std::string& scenePath, const double specs[8], bool postProcessing, const double* startXYZ,
+                     bool planLoopsAround, int device)
+    : postProcessing_(postProcessing), loops_(planLoopsAround), device_(device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("libipp: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) throw std::invalid_argument("libipp: bad device ordinal");
+    bind();
+    IPP_CUDA_CHECK(cudaDeviceGetAttribute(&numSMs_, cudaDevAttrMultiProcessorCount, device_));
+    IPP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    IPP_CUDA_CHECK(cudaEventCreate(&evStart_));
+    IPP_CUDA_CHECK(cudaEventCreate(&evStop_));
+    if (startXYZ) {
+        hasStart_ = true;
+        for (int k = 0; k < 3; ++k) start_[k] = startXYZ[k];
+    }
+
+    // ---- scene (SceneKeeper.cpp:65-71, TriangleData.cpp:41-72) ----
+    std::vector<float> tris;
+    load_mesh(scenePath, tris);
+    const int T = (int)(tris.size() / 9);
+    for (int k = 0; k < 3; ++k) { bbmin_[k] = INFINITY; bbmax_[k] = -INFINITY; }
+    for (size_t i = 0; i < tris.size(); ++i) {
+        int k = (int)(i % 3);
+        bbmin_[k] = std::min(bbmin_[k], tris[i]);
+        bbmax_[k] = std::max(bbmax_[k], tris[i]);
+    }
+    // float extents (osg::BoundingBox is float), OsgHelpers.cpp:499-511
+    double xl = std::fabs(bbmax_[0] - bbmin_[0]), yl = std::fabs(bbmax_[1] - bbmin_[1]), zl = std::fabs(bbmax_[2] - bbmin_[2]);
+    collisionPenalty_ = kCollisionPenaltyModifier * std::max(zl, std::max(xl, yl));
+    for (int k = 0; k < 3; ++k) sceneCenter_[k] = (double)((bbmin_[k] + bbmax_[k]) * 0.5f);  // bounding-sphere centre of one geode
+
+    float* d_verts = dalloc<float>(tris.size());
+    float* d_canon = dalloc<float>(tris.size());
+    float* d_centroid = dalloc<float>((size_t)T * 3);
+    uint8_t* d_degenerate = dalloc<uint8_t>(T);
+    const int64_t areaPad = round_up(std::max(T, 1), kTileTris);
+    nTiles_ = (int)(areaPad / kTileTris);
+    scene_.area = dalloc<double>(areaPad);
+    IPP_CUDA_CHECK(cudaMemsetAsync(scene_.area, 0, areaPad * sizeof(double), stream_));
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_verts, tris.data(), tris.size() * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    launch_mesh_prepare(d_verts, T, scene_.area, d_degenerate, d_canon, d_centroid, stream_);
+    areaHost_.resize(T);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(areaHost_.data(), scene_.area, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    build_bvh(d_verts, d_canon, d_centroid, d_degenerate, T, bbmin_, bbmax_, scene_, stream_);  // synchronises
+    nLaunches_ += 6;
+    cudaFree(d_verts);
+    cudaFree(d_canon);
+    cudaFree(d_centroid);
+    cudaFree(d_degenerate);
+    totalArea_ = 0;
+    for (int i = 0; i < T; ++i) totalArea_ += areaHost_[i];  // ascending-ID sum, TriangleData.cpp:65-72
+
+    // ---- sensor (CameraEstimator.cpp:53-63; argument swap at ImageViewerCaptureTool.cpp:22-26) ----
+    const double fovY = specs[1], aspect = specs[2] / specs[1];
+    const double PI = 3.14159265358979323846;
+    cam_.tanY = std::tan((fovY * 0.5) * PI / 180.0);
+    cam_.tanX = cam_.tanY * aspect;
+    cam_.H = (int)(unsigned)specs[3];
+    cam_.W = (int)(unsigned)(cam_.H * aspect);
+    cam_.zNear = (float)specs[4];
+    cam_.zFar = (float)specs[5];
+    cam_.front = specs[6] != 0;
+    cam_.down = specs[7] != 0;
+    cam_.sampleInterval = specs[0];
+    if (cam_.W <= 0 || cam_.H <= 0) throw std::invalid_argument("libipp: image size must be positive");
+    if (!(cam_.sampleInterval > 0)) throw std::invalid_argument("libipp: sampling interval must be positive");
+
+    // ---- scalars ----
+    d_scalars_ = dalloc<int>(8);
+    IPP_CUDA_CHECK(cudaHostAlloc((void**)&h_scalars_, 8 * sizeof(int), cudaHostAllocDefault));
+    d_visCounters_ = dalloc<unsigned long long>(2);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 2 * sizeof(unsigned long long), stream_));
+    d_angleOne_ = dalloc<float>(1);
+
+    // ---- candidate viewpoints (PlanInterpreterBoxOrder::divideIntoBoxes :193-251) ----
+    enumerate_grid_points(bbmin_, bbmax_, grid_);
+    {
+        const int64_t np = (int64_t)(grid_.points.size() / 3);
+        std::vector<uint8_t> close(np), vis(np);
+        boxesHitMesh(grid_.points.data(), np, kBoxSafetyMargin, close.data());
+        boxesHitMesh(grid_.points.data(), np, kCameraFarPlaneDist, vis.data());
+        assign_box_ids(grid_, close.data(), vis.data());
+    }
+    N_ = (int)(grid_.centres.size() / 3);
+    if (N_ == 0) throw std::logic_error("libipp: no candidate viewpoints around this mesh");
+    nKeys_ = (N_ + 1) * N_;
+    {
+        std::vector<double> pos(grid_.centres);
+        pos.push_back(start_[0]);
+        pos.push_back(start_[1]);
+        pos.push_back(start_[2]);
+        d_pos_ = dalloc<double>(pos.size());
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_pos_, pos.data(), pos.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        sync();
+    }
+
+    // ---- memo tables and the edge-bitmap row pool ----
+    d_coll_ = dalloc<uint8_t>(round_up(nKeys_, 4));
+    d_rowmap_ = dalloc<int>(nKeys_);
+    d_used_ = dalloc<uint8_t>(nKeys_);
+    d_newKeys_ = dalloc<int>(nKeys_);
+    rowWords_ = round_up((scene_.T + 31) / 32, 4);
+    {
+        size_t freeB = 0, totalB = 0;
+        IPP_CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
+        double frac = 0.70;
+        int64_t budget = (int64_t)(freeB * frac);
+        if (const char* e = getenv("IPP_CACHE_GB")) budget = std::min<int64_t>(budget, (int64_t)(atof(e) * 1e9));
+        // flag buffer for rendering batches comes out of the remaining memory
+        int64_t flagBudget = std::min<int64_t>((int64_t)2 << 30, (int64_t)(freeB * 0.05));
+        batchCap_ = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(65536, nKeys_), flagBudget / std::max(scene_.Tpad, 32)));
+        // worst-case tiles per edge keep the tile prefix sums inside int32
+        double diag = 0;
+        for (int k = 0; k < 3; ++k) {
+            double e = (double)(bbmax_[k] - bbmin_[k]) + 2 * kBoxPadding;
+            diag += e * e;
+        }
+        diag = std::sqrt(diag);
+        int64_t worstSnaps = ((int64_t)std::ceil(diag / cam_.sampleInterval) + 3) * 2;
+        int64_t tilesPerImage = (int64_t)((cam_.W + 31) / 32) * ((cam_.H + 31) / 32);
+        batchCap_ = (int)std::max<int64_t>(1, std::min<int64_t>(batchCap_, ((int64_t)1 << 30) / std::max<int64_t>(1, worstSnaps * tilesPerImage)));
+        rowCapacity_ = std::min<int64_t>(nKeys_, budget / (rowWords_ * 4));
+        if (rowCapacity_ < 1) throw std::runtime_error("libipp: not enough device memory for the edge-bitmap cache");
+    }
+    d_rows_ = dalloc<uint32_t>((size_t)(rowCapacity_ + 1) * rowWords_);
+    d_freeStack_ = dalloc<int>(rowCapacity_);
+    d_flags_ = dalloc<uint8_t>((size_t)batchCap_ * scene_.Tpad);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_flags_, 0, (size_t)batchCap_ * scene_.Tpad, stream_));
+    d_rowOfSlot_ = dalloc<int>(batchCap_);
+    d_counts_ = dalloc<int>(batchCap_ + 1);
+    d_snapOffset_ = dalloc<int>(batchCap_ + 1);
+    d_union_ = dalloc<uint32_t>(rowWords_);
+    clearMemo();
+
+    // ---- seeds and the energy limit (ProduceSimpleCirclingPlans :40-109, PlanEnergyEvaluator.cpp:40-46) ----
+    if (!postProcessing_) {
+        levelPlans_ = single_level_circling_plans(grid_);
+        completePlans_ = complete_circling_plans(levelPlans_);
+        if (completePlans_.empty()) throw std::logic_error("libipp: no circling plans could be generated for this mesh");
+        // energy of the longest circling plan, decoded WITHOUT loop closure (decodeAndCalculateEnergyUsage is
+        // called directly, not through evaluatePlan)
+        const Plan& front = completePlans_.front();
+        std::vector<int32_t> ids;
+        for (const auto& g : front) ids.push_back((int32_t)(size_t)(g[0] + 0.5));  // -1 -> 0, SURVEY A.11
+        std::vector<int64_t> off = {0, (int64_t)ids.size()};
+        double fit[4];
+        bool savedLoops = loops_;
+        loops_ = false;
+        maxAllowedEnergy_ = -INFINITY;  // energy only: with this limit every plan fails the gate, no coverage work
+        evaluatePopulationHost(ids.data(), nullptr, off.data(), 1, true, false, fit, nullptr);
+        loops_ = savedLoops;
+        maxAllowedEnergy_ = fit[1] * kMaxEnergyMultiplier;
+    } else {
+        maxAllowedEnergy_ = -1;
+    }
+    int64_t c[8];
+    counters(c, true);
+}
+
+Evaluator::~Evaluator() {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    free_bvh(scene_);
+    cudaFree(scene_.area);
+    cudaFree(d_pos_); cudaFree(d_coll_); cudaFree(d_rowmap_); cudaFree(d_used_); cudaFree(d_newKeys_);
+    cudaFree(d_scalars_); cudaFreeHost(h_scalars_); cudaFree(d_rows_); cudaFree(d_freeStack_);
+    cudaFree(d_flags_); cudaFree(d_rowOfSlot_); cudaFree(d_counts_); cudaFree(d_snapOffset_);
+    cudaFree(d_snaps_); cudaFree(d_ntiles_); cudaFree(d_tileOffset_); cudaFree(d_scanTmp_);
+    cudaFree(d_visCounters_); cudaFree(d_angleOne_);
+    cudaFree(d_ids_); cudaFree(d_offsets_); cudaFree(d_fitness_); cudaFree(d_active_); cudaFree(d_union_);
+    cudaFree(d_flushBuf_);
+    for (auto& e : pendingEv_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : freeEv_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaEventDestroy(evStart_);
+    cudaEventDestroy(evStop_);
+    cudaStreamDestroy(stream_);
+}
+
+// ---------------------------------------------------------------------------------------------
+void Evaluator::readScalars() {
+    IPP_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, d_scalars_, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+int Evaluator::readInt(const int* d) {
+    IPP_CUDA_CHECK(cudaMemcpyAsync(h_scalars_, d, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    return h_scalars_[0];
+}
+
+void Evaluator::groupBegin(int g) {
+    if (!profiling_) return;
+    EvPair e;
+    if (!freeEv_.empty()) {
+        e = freeEv_.back();
+        freeEv_.pop_back();
+    } else {
+        IPP_CUDA_CHECK(cudaEventCreate(&e.a));
+        IPP_CUDA_CHECK(cudaEventCreate(&e.b));
+    }
+    e.group = g;
+    IPP_CUDA_CHECK(cudaEventRecord(e.a, stream_));
+    pendingEv_.push_back(e);
+}
+void Evaluator::groupEnd(int g) {
+    if (!profiling_) return;
+    IPP_CUDA_CHECK(cudaEventRecord(pendingEv_.back().b, stream_));
+    groupLaunches_[g]++;
+    if (pendingEv_.size() > 4096) harvestTimings(false);
+}
+void Evaluator::harvestTimings(bool wait) {
+    size_t keep = 0;
+    for (size_t i = 0; i < pendingEv_.size(); ++i) {
+        EvPair& e = pendingEv_[i];
+        cudaError_t q = wait ? cudaEventSynchronize(e.b) : cudaEventQuery(e.b);
+        if (q == cudaSuccess) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e.a, e.b);
+            groupMs_[e.group] += ms;
+            freeEv_.push_back(e);
+        } else {
+            pendingEv_[keep++] = e;
+        }
+    }
+    pendingEv_.resize(keep);
+    cudaGetLastError();
+}
+void Evaluator::kernelTime(int which, double* ms, int64_t* launches, bool reset) {
+    if (which < 0 || which >= KG_COUNT) throw std::invalid_argument("libipp: bad kernel group");
+    bind();
+    harvestTimings(true);
+    *ms = groupMs_[which];
+    *launches = groupLaunches_[which];
+    if (reset) {
+        groupMs_[which] = 0;
+        groupLaunches_[which] = 0;
+    }
+}
+void Evaluator::counters(int64_t out[8], bool reset) {
+    bind();
+    unsigned long long rays = 0;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(&rays, d_visCounters_, sizeof(rays), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    out[0] = nLaunches_; out[1] = (int64_t)rays; out[2] = nSnapshots_; out[3] = nEdgesRendered_;
+    out[4] = nCollisionQueries_; out[5] = nReduceLaunches_; out[6] = nPlansReduced_; out[7] = nRowsRead_;
+    if (reset) {
+        nLaunches_ = nSnapshots_ = nEdgesRendered_ = nCollisionQueries_ = nReduceLaunches_ = nPlansReduced_ = nRowsRead_ = 0;
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, sizeof(unsigned long long), stream_));
+    }
+}
+void Evaluator::timerStart() {
+    bind();
+    IPP_CUDA_CHECK(cudaEventRecord(evStart_, stream_));
+}
+double Evaluator::timerStop() {
+    bind();
+    IPP_CUDA_CHECK(cudaEventRecord(evStop_, stream_));
+    IPP_CUDA_CHECK(cudaEventSynchronize(evStop_));
+    float ms = 0;
+    IPP_CUDA_CHECK(cudaEventElapsedTime(&ms, evStart_, evStop_));
+    return ms;
+}
+void Evaluator::flushL2() {
+    bind();
+    if (!d_flushBuf_) {
+        flushWords_ = (int64_t)(256 << 20) / 4;  // 256 MiB > 126 MB L2
+        d_flushBuf_ = dalloc<uint32_t>(flushWords_);
+    }
+    launch_flush(d_flushBuf_, flushWords_, stream_);
+    nLaunches_++;
+}
+
+void Evaluator::exclusiveScan(const int* d_in, int* d_out, int n) {
+    size_t need = scan_tmp_bytes(n);
+    if (need > scanTmpBytes_) {
+        cudaFree(d_scanTmp_);
+        scanTmpBytes_ = need * 2;
+        IPP_CUDA_CHECK(cudaMalloc(&d_scanTmp_, scanTmpBytes_));
+    }
+    exclusive_scan_i32(d_in, d_out, n, d_scanTmp_, scanTmpBytes_, stream_);
+    nLaunches_++;
+}
+
+void Evaluator::ensurePlanBuffers(int64_t pop, int64_t nGenes) {
+    if (pop > popCap_) {
+        cudaFree(d_offsets_);
+        cudaFree(d_fitness_);
+        popCap_ = pop + pop / 4 + 16;
+        d_offsets_ = dalloc<int64_t>(popCap_ + 1);
+        d_fitness_ = dalloc<double>(popCap_ * 4);
+    }
+    if (nGenes > geneCap_) {
+        cudaFree(d_ids_);
+        geneCap_ = nGenes + nGenes / 4 + 16;
+        d_ids_ = dalloc<int32_t>(geneCap_);
+    }
+}
+void Evaluator::ensureSnapBuffers(int64_t nSnaps) {
+    if (nSnaps + 1 > snapCap_) {
+        cudaFree(d_snaps_);
+        cudaFree(d_ntiles_);
+        cudaFree(d_tileOffset_);
+        snapCap_ = nSnaps + nSnaps / 4 + 64;
+        d_snaps_ = dalloc<Snapshot>(snapCap_);
+        d_ntiles_ = dalloc<int>(snapCap_);
+        d_tileOffset_ = dalloc<int>(snapCap_);
+    }
+}
+
+void Evaluator::clearMemo() {
+    bind();
+    launch_fill_u8(d_coll_, round_up(nKeys_, 4), 0xFF, stream_);
+    launch_fill_i32(d_rowmap_, nKeys_, -1, stream_);
+    launch_iota_i32(d_freeStack_, rowCapacity_, stream_);
+    int top = (int)rowCapacity_;
+    h_scalars_[1] = top;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_scalars_ + 1, h_scalars_ + 1, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    sync();
+    nLaunches_ += 3;
+    liveRows_ = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 + K4 + pack for n freshly claimed keys (batched by the flag buffer capacity)
+// ---------------------------------------------------------------------------------------------
+void Evaluator::renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot) {
+    // samples per edge -> snapshot offsets
+    launch_count_snapshots(d_keys, n, d_pos_, N_, cam_, d_counts_, stream_);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_counts_ + n, 0, sizeof(int), stream_));
+    exclusiveScan(d_counts_, d_snapOffset_, n + 1);
+    int nSnaps = readInt(d_snapOffset_ + n);
+    ensureSnapBuffers(nSnaps);
+    groupBegin(KG_PLAN);
+    launch_fill_snapshots(d_keys, d_angles, n, d_pos_, N_, sceneCenter_, cam_, scene_, d_snapOffset_, d_snaps_, d_ntiles_, stream_);
+    groupEnd(KG_PLAN);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_ntiles_ + nSnaps, 0, sizeof(int), stream_));
+    exclusiveScan(d_ntiles_, d_tileOffset_, nSnaps + 1);
+    int totalTiles = readInt(d_tileOffset_ + nSnaps);
+    groupBegin(KG_VISIBILITY);
+    launch_visibility(scene_, cam_, d_snaps_, d_tileOffset_, nSnaps, totalTiles, d_flags_, nullptr, d_visCounters_, stream_);
+    groupEnd(KG_VISIBILITY);
+    groupBegin(KG_PACK);
+    launch_pack_rows(d_flags_, n, scene_.Tpad, d_rowOfSlot, d_rows_, rowWords_, stream_);
+    groupEnd(KG_PACK);
+    nLaunches_ += 5;
+    nSnapshots_ += nSnaps;
+    nEdgesRendered_ += n;
+}
+
+void Evaluator::renderNewEdges(int nNew, const float* d_angles) {
+    for (int b0 = 0; b0 < nNew; b0 += batchCap_) {
+        int n = std::min(batchCap_, nNew - b0);
+        launch_assign_rows(d_newKeys_ + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
+        renderBatch(d_newKeys_ + b0, d_angles ? d_angles + b0 : nullptr, n, d_rowOfSlot_);
+        launch_publish_rows(d_newKeys_ + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
+        nLaunches_ += 2;
+    }
+    liveRows_ += nNew;
+}
+
+// ---------------------------------------------------------------------------------------------
+void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t pop,
+                                         int64_t nGenes, bool memo, bool noLimit, double* d_fitness, uint32_t* unionBitmapHost) {
+    bind();
+    if (d_angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
+    if (pop <= 0) return;
+    if (pop > activeCap_) {
+        cudaFree(d_active_);
+        activeCap_ = pop + pop / 4 + 16;
+        d_active_ = dalloc<uint8_t>(activeCap_);
+    }
+    PlanMarkArgs mk;
+    mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
+    mk.active = nullptr; mk.coll = d_coll_; mk.rowmap = nullptr; mk.used = nullptr; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
+    mk.errFlag = d_scalars_ + 3;
+
+    // 1. collision flags never seen before -> K5 (also validates the box ids: assert at PlanInterpreterBoxOrder.cpp:282)
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 3, 0, sizeof(int), stream_));
+    groupBegin(KG_PLAN);
+    launch_mark_collisions(mk, stream_);
+    groupEnd(KG_PLAN);
+    nLaunches_++;
+    readScalars();
+    if (h_scalars_[3]) throw std::out_of_range("libipp: box id out of range");
+    int nColl = h_scalars_[0];
+    if (nColl > 0) {
+        groupBegin(KG_COLLISION);
+        launch_collide_keys(scene_, d_newKeys_, nColl, d_pos_, N_, d_coll_, stream_);
+        groupEnd(KG_COLLISION);
+        nLaunches_++;
+        nCollisionQueries_ += nColl;
+    }
+
+    // 2. energy + gate
+    PlanEnergyArgs en;
+    en.ids = d_ids; en.offsets = d_offsets; en.pop = pop; en.N = N_; en.hasStart = hasStart_; en.loops = loops_;
+    en.pos = d_pos_; en.coll = d_coll_; en.collisionPenalty = collisionPenalty_; en.maxEnergy = maxAllowedEnergy_;
+    en.disableLimit = noLimit; en.fitness = d_fitness; en.active = d_active_;
+    groupBegin(KG_PLAN);
+    launch_energy(en, stream_);
+    nLaunches_++;
+
+    // 3. edge bitmaps never seen before -> K3, K4, pack
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+    mk.active = d_active_; mk.coll = nullptr; mk.rowmap = d_rowmap_;
+    const bool wantUsed = unionBitmapHost != nullptr;
+    if (wantUsed) {
+        launch_fill_u8(d_used_, nKeys_, 0, stream_);
+        mk.used = d_used_;
+        nLaunches_++;
+    }
+    launch_mark_rows(mk, stream_);
+    groupEnd(KG_PLAN);
+    nLaunches_++;
+    readScalars();
+    int nNew = h_scalars_[0];
+    if (nNew > 0) {
+        int freeRows = h_scalars_[1];
+        if (nNew > freeRows)
+            throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
+                                     " free rows); call updateMemoisedEdges or evaluate a smaller batch");
+        renderNewEdges(nNew, nullptr);
+    }
+
+    // 4. OR + area-weighted popcount
+    PlanReduceArgs rd;
+    rd.ids = d_ids; rd.offsets = d_offsets; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
+    rd.active = d_active_; rd.rowmap = d_rowmap_; rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
+    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness;
+    groupBegin(KG_REDUCE);
+    launch_plan_reduce(rd, numSMs_, stream_);
+    groupEnd(KG_REDUCE);
+    nLaunches_++;
+    nReduceLaunches_++;
+    nPlansReduced_ += pop;
+
+    if (wantUsed) {
+        launch_union_rows(d_used_, nKeys_, d_rowmap_, d_rows_, rowWords_, d_union_, stream_);
+        nLaunches_++;
+        IPP_CUDA_CHECK(cudaMemcpyAsync(unionBitmapHost, d_union_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
+        sync();
+    }
+    if (!memo && nNew > 0) {
+        // memoization == false: edges rendered for this call are not remembered (evaluatePlanInternal,
+        // PlanCoverageEstimator.cpp:128-151); hand their rows back
+        // (reuse the collector with used = 1 everywhere except the new keys)
+        std::vector<int> keys(nNew);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(keys.data(), d_newKeys_, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        sync();
+        std::vector<uint8_t> used(nKeys_, 1);
+        for (int k : keys) used[k] = 0;
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_used_, used.data(), nKeys_, cudaMemcpyHostToDevice, stream_));
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 2, 0, sizeof(int), stream_));
+        launch_gc_rows(d_rowmap_, d_used_, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
+        nLaunches_ += 2;
+        liveRows_ = readInt(d_scalars_ + 2);
+    }
+}
+
+void Evaluator::evaluatePopulationHost(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo,
+                                       bool noLimit, double* fitness, uint32_t* unionBitmap) {
+    bind();
+    if (pop <= 0) return;
+    if (angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
+    const int64_t nGenes = offsets[pop] - offsets[0];
+    if (offsets[0] != 0) throw std::invalid_argument("libipp: offsets[0] must be 0");
+    ensurePlanBuffers(pop, nGenes);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_ids_, ids, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_offsets_, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+    evaluatePopulationDevice(d_ids_, nullptr, d_offsets_, pop, nGenes, memo, noLimit, d_fitness_, unionBitmap);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, d_fitness_, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+int64_t Evaluator::updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop) {
+    bind();
+    if (angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
+    const int64_t nGenes = pop > 0 ? offsets[pop] : 0;
+    for (int64_t g = 0; g < nGenes; ++g)
+        if (ids[g] < 0 || ids[g] >= N_) throw std::out_of_range("libipp: box id out of range");
+    ensurePlanBuffers(std::max<int64_t>(pop, 1), std::max<int64_t>(nGenes, 1));
+    launch_fill_u8(d_used_, nKeys_, 0, stream_);
+    if (pop > 0) {
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_ids_, ids, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_offsets_, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+        // keys of the raw population: "start-first" only exists with a start location and the loop-closing edge is
+        // never part of the set (PlanCoverageEstimator.cpp:284-310)
+        PlanMarkArgs mk;
+        mk.ids = d_ids_; mk.offsets = d_offsets_; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = false;
+        mk.active = nullptr; mk.coll = nullptr; mk.rowmap = nullptr; mk.used = d_used_; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
+        mk.errFlag = d_scalars_ + 3;
+        launch_mark_rows(mk, stream_);
+        nLaunches_++;
+    }
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 2, 0, sizeof(int), stream_));
+    launch_gc_rows(d_rowmap_, d_used_, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
+    nLaunches_ += 2;
+    liveRows_ = readInt(d_scalars_ + 2);
+    return liveRows_;
+}
+
+// InterpretPlan, PlanInterpreterBoxOrder.cpp:301-324 (host twin of the device decode; used for export only)
+void Evaluator::interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs) const {
+    *nPos = 0;
+    *nDirs = 0;
+    if (n == 0) return;
+    D3 center = d3(sceneCenter_[0], sceneCenter_[1], sceneCenter_[2]);
+    std::vector<D3> p;
+    if (hasStart_) p.push_back(d3(start_[0], start_[1], start_[2]));
+    int nd = 0;
+    for (int i = 0; i < n; ++i) {
+        size_t id = (size_t)(genes[(size_t)i * width] + 0.5);
+        if (id >= (size_t)N_) throw std::out_of_range("libipp: box id out of range");
+        float off = width > 1 ? (float)genes[(size_t)i * width + 1] : 0.f;
+        D3 cur = d3(grid_.centres[3 * id], grid_.centres[3 * id + 1], grid_.centres[3 * id + 2]);
+        if (!p.empty()) {
+            D3 h = sensor_direction(p.back(), cur, center, off);
+            dirs[3 * nd] = h.x; dirs[3 * nd + 1] = h.y; dirs[3 * nd + 2] = h.z;
+            nd++;
+        }
+        p.push_back(cur);
+    }
+    for (size_t i = 0; i < p.size(); ++i) { pos[3 * i] = p[i].x; pos[3 * i + 1] = p[i].y; pos[3 * i + 2] = p[i].z; }
+    *nPos = (int)p.size();
+    *nDirs = nd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test hooks
+// ---------------------------------------------------------------------------------------------
+void Evaluator::edgeBitmap(int prev, int curr, double angle, uint32_t* out) {
+    bind();
+    if (prev == -1) {
+        if (!hasStart_) throw std::invalid_argument("libipp: no start location");
+        prev = N_;
+    }
+    if (prev < 0 || prev > N_ || curr < 0 || curr >= N_) throw std::out_of_range("libipp: box id out of range");
+    int key = prev * N_ + curr;
+    float a = (float)angle;
+    // rendered into the scratch row (index rowCapacity_), the memo is left untouched
+    int scratch = (int)rowCapacity_;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_newKeys_, &key, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowOfSlot_, &scratch, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_angleOne_, &a, sizeof(float), cudaMemcpyHostToDevice, stream_));
+    renderBatch(d_newKeys_, d_angleOne_, 1, d_rowOfSlot_);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(out, d_rows_ + (size_t)scratch * rowWords_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
+
+void Evaluator::edgesCollide(const double* edges, int64_t n, uint8_t* out) {
+    bind();
+    if (n <= 0) return;
+    double* d_e = dalloc<double>((size_t)n * 6);
+    uint8_t* d_o = dalloc<uint8_t>(n);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_e, edges, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    launch_collide_xyz(scene_, d_e, n, d_o, stream_);
+    nLaunches_++;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(out, d_o, n, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    cudaFree(d_e);
+    cudaFree(d_o);
+}
+
+void Evaluator::boxesHitMesh(const double* centres, int64_t n, double half, uint8_t* out) {
+    bind();
+    if (n <= 0) return;
+    double* d_c = dalloc<double>((size_t)n * 3);
+    uint8_t* d_o = dalloc<uint8_t>(n);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_c, centres, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    launch_boxes_hit(scene_, d_c, n, half, d_o, stream_);
+    nLaunches_++;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(out, d_o, n, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    cudaFree(d_c);
+    cudaFree(d_o);
+}
+
+void Evaluator::renderIds(const double* eye, const double* center, const double* up, int32_t* out) {
+    bind();
+    ensureSnapBuffers(2);
+    int32_t* d_img = dalloc<int32_t>((size_t)cam_.W * cam_.H);
+    launch_single_snapshot(d_snaps_, eye, center, up, cam_, scene_, d_ntiles_, stream_);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_ntiles_ + 1, 0, sizeof(int), stream_));
+    exclusiveScan(d_ntiles_, d_tileOffset_, 2);
+    int totalTiles = readInt(d_tileOffset_ + 1);
+    launch_visibility(scene_, cam_, d_snaps_, d_tileOffset_, 1, totalTiles, d_flags_, d_img, d_visCounters_, stream_);
+    int scratch = (int)rowCapacity_;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowOfSlot_, &scratch, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    launch_pack_rows(d_flags_, 1, scene_.Tpad, d_rowOfSlot_, d_rows_, rowWords_, stream_);  // clears the flags
+    nLaunches_ += 4;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(out, d_img, (size_t)cam_.W * cam_.H * 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    cudaFree(d_img);
+}
+
+void Evaluator::bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches) {
+    bind();
+    *mismatches = 0;
+    if (n <= 0) return;
+    float* d_r = dalloc<float>((size_t)n * 6);
+    int32_t* d_a = dalloc<int32_t>(n);
+    int32_t* d_b = dalloc<int32_t>(n);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_r, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    launch_bvh_selftest(scene_, d_r, n, d_a, d_b, stream_);
+    nLaunches_++;
+    std::vector<int32_t> b(n);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(outIds, d_a, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    IPP_CUDA_CHECK(cudaMemcpyAsync(b.data(), d_b, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
+    for (int64_t i = 0; i < n; ++i)
+        if (outIds[i] != b[i]) (*mismatches)++;
+    cudaFree(d_r);
+    cudaFree(d_a);
+    cudaFree(d_b);
+}
+
+}  // namespace ipp

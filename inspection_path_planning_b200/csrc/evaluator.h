@@ -1,0 +1,139 @@
+// evaluator.h -- host-side owner of one B200-resident plan evaluator (the object behind ipp_t).
+// Mirrors PlanCoverageEstimator (plan_evaluator/Evaluator/src/PlanCoverageEstimator.h:51-165).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "planner.h"
+
+namespace ipp {
+
+struct Comm;  // comm.cpp
+
+enum KernelGroup { KG_REDUCE = 0, KG_VISIBILITY = 1, KG_COLLISION = 2, KG_PACK = 3, KG_PLAN = 4, KG_COUNT = 5 };
+
+class Evaluator {
+   public:
+    Evaluator(const std::string& scenePath, const double sensorSpecs[8], bool postProcessing, const double* startXYZ, bool planLoopsAround,
+              int device);
+    ~Evaluator();
+
+    // ---- reference API ----
+    int numBoxes() const { return N_; }
+    int64_t numTriangles() const { return scene_.T; }
+    int64_t bitmapWords() const { return (scene_.T + 31) / 32; }
+    double maxAllowedEnergy() const { return maxAllowedEnergy_; }
+    const std::vector<Plan>& simplePlans() const { return completePlans_; }
+    void evaluatePopulationHost(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo, bool noLimit,
+                                double* fitness, uint32_t* unionBitmap);
+    void evaluatePopulationDevice(const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t pop, int64_t nGenes,
+                                  bool memo, bool noLimit, double* d_fitness, uint32_t* unionBitmapHost);
+    int64_t updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
+    int64_t memoSize() const { return liveRows_; }
+    void clearMemo();
+    void interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs) const;
+
+    // ---- test hooks ----
+    void edgeBitmap(int prev, int curr, double angle, uint32_t* out);
+    void edgesCollide(const double* edges, int64_t n, uint8_t* out);
+    void boxesHitMesh(const double* centres, int64_t n, double half, uint8_t* out);
+    void renderIds(const double* eye, const double* center, const double* up, int32_t* out);
+    void bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches);
+
+    // ---- plumbing ----
+    void sync() { IPP_CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+    void timerStart();
+    double timerStop();
+    void flushL2();
+    void counters(int64_t out[8], bool reset);
+    void kernelTime(int which, double* ms, int64_t* launches, bool reset);
+    void setProfiling(bool on) { profiling_ = on; }
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return device_; }
+    void bind() const { IPP_CUDA_CHECK(cudaSetDevice(device_)); }
+
+    // scene facts
+    double totalArea_ = 0, collisionPenalty_ = 0;
+    double sceneCenter_[3] = {0, 0, 0};
+    float bbmin_[3], bbmax_[3];
+    std::vector<double> areaHost_;
+    ViewpointGrid grid_;
+    CameraParams cam_;
+    bool postProcessing_ = false, hasStart_ = false, loops_ = false;
+    double start_[3] = {0, 0, 0};
+    Comm* comm_ = nullptr;
+
+   private:
+    void renderNewEdges(int nNew, const float* d_angles);
+    void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
+    void ensurePlanBuffers(int64_t pop, int64_t nGenes);
+    void ensureSnapBuffers(int64_t nSnaps);
+    int readInt(const int* d);
+    void readScalars();
+    void groupBegin(int g);
+    void groupEnd(int g);
+    void harvestTimings(bool wait);
+    void exclusiveScan(const int* d_in, int* d_out, int n);
+
+    int device_ = 0, numSMs_ = 148;
+    cudaStream_t stream_ = nullptr;
+    DeviceScene scene_;
+    int N_ = 0;          // candidate viewpoints
+    int nKeys_ = 0;      // (N+1) * N directed edge keys, row N of the position table = start location
+    double maxAllowedEnergy_ = -1;
+    std::vector<Plan> levelPlans_, completePlans_;
+
+    // device tables
+    double* d_pos_ = nullptr;      // (N+1) x 3
+    uint8_t* d_coll_ = nullptr;    // nKeys (padded to 4)
+    int* d_rowmap_ = nullptr;      // nKeys
+    uint8_t* d_used_ = nullptr;    // nKeys
+    int* d_newKeys_ = nullptr;     // nKeys
+    int* d_scalars_ = nullptr;     // [0] newCount, [1] freeTop, [2] live, [3] scratch
+    int* h_scalars_ = nullptr;     // pinned mirror
+    uint32_t* d_rows_ = nullptr;   // row pool: (capacity + 1) rows, the last one is scratch
+    int64_t rowWords_ = 0, rowCapacity_ = 0;
+    int* d_freeStack_ = nullptr;
+    int64_t liveRows_ = 0;
+    int nTiles_ = 0;
+
+    // render batch buffers
+    int batchCap_ = 0;
+    uint8_t* d_flags_ = nullptr;
+    int *d_rowOfSlot_ = nullptr, *d_counts_ = nullptr, *d_snapOffset_ = nullptr;
+    Snapshot* d_snaps_ = nullptr;
+    int *d_ntiles_ = nullptr, *d_tileOffset_ = nullptr;
+    int64_t snapCap_ = 0;
+    void* d_scanTmp_ = nullptr;
+    size_t scanTmpBytes_ = 0;
+    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] chunk cursor
+    float* d_angleOne_ = nullptr;
+
+    // plan buffers (host-pointer entry point)
+    int32_t* d_ids_ = nullptr;
+    int64_t* d_offsets_ = nullptr;
+    double* d_fitness_ = nullptr;
+    uint8_t* d_active_ = nullptr;
+    int64_t popCap_ = 0, geneCap_ = 0, activeCap_ = 0;
+    uint32_t* d_union_ = nullptr;
+
+    // timing
+    cudaEvent_t evStart_ = nullptr, evStop_ = nullptr;
+    struct EvPair { cudaEvent_t a, b; int group; };
+    std::vector<EvPair> pendingEv_, freeEv_;
+    double groupMs_[KG_COUNT] = {0, 0, 0, 0, 0};
+    int64_t groupLaunches_[KG_COUNT] = {0, 0, 0, 0, 0};
+    bool profiling_ = true;
+    uint32_t* d_flushBuf_ = nullptr;
+    int64_t flushWords_ = 0;
+    // counters
+    int64_t nLaunches_ = 0, nSnapshots_ = 0, nEdgesRendered_ = 0, nCollisionQueries_ = 0, nReduceLaunches_ = 0, nPlansReduced_ = 0,
+            nRowsRead_ = 0;
+};
+
+
+}  // namespace ipp

@@ -1,0 +1,98 @@
+// kernels.h -- launch wrappers of every CUDA kernel in libipp.so (one per translation unit group).
+#pragma once
+#include "common.cuh"
+
+namespace ipp {
+
+struct PlanMarkArgs {
+    const int* ids;
+    const int64_t* offsets;
+    int64_t pop;
+    int N;
+    bool hasStart, loops;
+    const uint8_t* active;  // nullable: only plans with active[p] != 0
+    uint8_t* coll;          // collision flags per key: 0xFF unknown, 0xFE pending, 0 / 1
+    int* rowmap;            // bitmap row per key: -1 unknown, -2 pending, >= 0 row
+    uint8_t* used;          // nullable: set to 1 for every key touched
+    int* newKeys;
+    int* newCount;
+    int* errFlag;  // set to 1 when a box id is out of range
+};
+
+struct PlanEnergyArgs {
+    const int* ids;
+    const int64_t* offsets;
+    int64_t pop;
+    int N;
+    bool hasStart, loops;
+    const double* pos;  // (N+1) x 3, row N = start location
+    const uint8_t* coll;
+    double collisionPenalty, maxEnergy;
+    bool disableLimit;
+    double* fitness;  // pop x 4
+    uint8_t* active;  // pop
+};
+
+struct PlanReduceArgs {
+    const int* ids;
+    const int64_t* offsets;
+    int64_t pop;
+    int N;
+    bool hasStart, loops;
+    const uint8_t* active;
+    const int* rowmap;
+    const uint32_t* rows;  // row pool
+    int64_t rowWords;      // words per row (multiple of 4)
+    const double* area;    // padded to nTiles * kTileTris
+    int nTiles;
+    double totalArea;
+    double* fitness;
+};
+
+// exact.cu (-fmad=false)
+void launch_mesh_prepare(const float* d_verts, int T, double* d_area, uint8_t* d_degenerate, float* d_canon, float* d_centroid, cudaStream_t st);
+void launch_collide_keys(const DeviceScene& sc, const int* d_keys, int n, const double* d_pos, int N, uint8_t* d_coll, cudaStream_t st);
+void launch_collide_xyz(const DeviceScene& sc, const double* d_edges, int64_t n, uint8_t* d_out, cudaStream_t st);
+void launch_boxes_hit(const DeviceScene& sc, const double* d_centres, int64_t n, double s, uint8_t* d_out, cudaStream_t st);
+void launch_count_snapshots(const int* d_keys, int n, const double* d_pos, int N, const CameraParams& cam, int* d_counts, cudaStream_t st);
+void launch_fill_snapshots(const int* d_keys, const float* d_angles, int n, const double* d_pos, int N, const double center[3],
+                           const CameraParams& cam, const DeviceScene& sc, const int* d_snapOffset, Snapshot* d_snaps, int* d_ntiles,
+                           cudaStream_t st);
+void launch_single_snapshot(Snapshot* d_snap, const double eye[3], const double center[3], const double up[3], const CameraParams& cam,
+                            const DeviceScene& sc, int* d_ntiles, cudaStream_t st);
+void launch_mark_collisions(const PlanMarkArgs& a, cudaStream_t st);
+void launch_energy(const PlanEnergyArgs& a, cudaStream_t st);
+void launch_mark_rows(const PlanMarkArgs& a, cudaStream_t st);
+void launch_gc_rows(int* d_rowmap, const uint8_t* d_used, int nKeys, int* d_freeStack, int* d_freeTop, int* d_live, cudaStream_t st);
+void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, cudaStream_t st);
+void launch_publish_rows(const int* d_keys, const int* d_rows, int n, int* d_rowmap, cudaStream_t st);
+
+// lbvh.cu
+// Builds the BVH over the non-degenerate triangles.  d_verts / d_canon: T x 9 floats (file / canonical vertex order).
+void build_bvh(const float* d_verts, const float* d_canon, const float* d_centroid, const uint8_t* d_degenerate, int T,
+               const float bbmin[3], const float bbmax[3], DeviceScene& sc, cudaStream_t st);
+void free_bvh(DeviceScene& sc);
+
+// visibility.cu
+// Casts one ray through every pixel centre of the macro tiles listed for the snapshots and sets flags[slot * Tpad + id] = 1
+// for the nearest triangle.  d_tileOffset = exclusive scan of tiles per snapshot, totalTiles its sum.
+void launch_visibility(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_tileOffset, int nSnaps,
+                       int64_t totalTiles, uint8_t* d_flags, int32_t* d_idImage /*nullable test hook*/,
+                       unsigned long long* d_rayCounter, cudaStream_t st);
+// flags[slot][Tpad] (bytes) -> bitmap rows; clears the flags
+void launch_pack_rows(uint8_t* d_flags, int nSlots, int Tpad, const int* d_rowOfSlot, uint32_t* d_rows, int64_t rowWords, cudaStream_t st);
+void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, int32_t* d_idsBvh, int32_t* d_idsBrute, cudaStream_t st);
+int visibility_grid_blocks();
+size_t scan_tmp_bytes(int n);
+void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);
+
+// plan_reduce.cu (-fmad=false)
+void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st);
+void launch_union_rows(const uint8_t* d_used, int nKeys, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union,
+                       cudaStream_t st);
+void launch_fill_u8(uint8_t* p, int64_t n, uint8_t v, cudaStream_t st);
+void launch_fill_i32(int* p, int64_t n, int v, cudaStream_t st);
+void launch_iota_i32(int* p, int64_t n, cudaStream_t st);
+void launch_flush(uint32_t* p, int64_t nWords, cudaStream_t st);
+
+}  // namespace ipp

@@ -1,0 +1,208 @@
+// plan_reduce.cu -- K6 plan_reduce: the HBM-bound kernel of the warm path.
+//
+// Per plan that passed the energy gate: OR the memoised seen-triangle bitmaps of its E edges
+// (evaluateMemoisedPlan, PlanCoverageEstimator.cpp:43-118) and turn the union into the coverage score
+// 1 - sum(area[i] * bit[i]) / totalArea (TriangleData::calculateAndColorCoverage, TriangleData.cpp:155-194).
+//
+// Layout: one warp per plan, 8 plans per CTA marching together over tiles of 128 bitmap words (4096
+// triangles).  Per tile a lane streams one uint4 (16 B) of each of the E rows straight from HBM --
+// E independent 512-byte coalesced requests in flight per warp -- and ORs them in registers; the 4096
+// fp64 areas of the tile are staged once per CTA in shared memory with cp.async (double buffered) and
+// shared by the 8 plans; the union words are broadcast with shuffles, lane b adds area[32 w + b] when bit
+// b of word w is set (ballot-selected non-zero words only), and a final shuffle tree gives the covered
+// area.  No atomics, no per-individual bitmap ever touches memory.
+// Algorithmic bytes per plan: E * 4 * ceil(T/32) + 4 * (V + 1) + 32  (SURVEY 8d).
+// Compiled with -fmad=false (only fp64 adds and one division are involved).
+#include "kernels.h"
+
+namespace ipp {
+
+namespace {
+
+constexpr int kPlansPerCta = 8;
+constexpr int kThreads = kPlansPerCta * 32;
+constexpr int kSmemBytes = 2 * kTileTris * (int)sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    // rows are read once per plan and never reused by this CTA: do not allocate in L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_plan_reduce(PlanReduceArgs a) {
+    extern __shared__ __align__(16) double s_area_raw[];  // 2 x 32 KB
+    double(*s_area)[kTileTris] = (double(*)[kTileTris])s_area_raw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rowVec = (int)(a.rowWords / 4);  // uint4 per row
+    for (long long p0 = (long long)blockIdx.x * kPlansPerCta; p0 < a.pop; p0 += (long long)gridDim.x * kPlansPerCta) {
+        long long p = p0 + warp;
+        // ---- this warp's plan: edge list -> row indices (lane e holds edge e of the current 32-edge chunk) ----
+        int nEdges = 0;
+        long long lo = 0;
+        int nGenes = 0;
+        bool act = false;
+        if (p < a.pop && a.active[p]) {
+            lo = a.offsets[p];
+            nGenes = (int)(a.offsets[p + 1] - lo);
+            int m = nGenes == 0 ? 0 : nGenes + (a.hasStart ? 1 : 0) + (a.loops ? 1 : 0);
+            nEdges = m > 0 ? m - 1 : 0;
+            act = true;
+        }
+        auto boxAt = [&](int k) -> int {  // position k of the plan (N = start location)
+            if (a.hasStart) {
+                if (k == 0) return a.N;
+                k -= 1;
+            }
+            return k < nGenes ? a.ids[lo + k] : a.ids[lo];
+        };
+        auto rowOfEdge = [&](int e) -> int {  // edge e joins positions e and e + 1
+            if (e >= nEdges) return -1;
+            return a.rowmap[boxAt(e) * a.N + boxAt(e + 1)];
+        };
+        // an area tile is needed by the CTA if any of its plans is active
+        int anyAct = __syncthreads_or(act ? 1 : 0);
+        if (!anyAct) continue;
+
+        double acc = 0.0;
+        // prefetch area tile 0
+        {
+            const double* src = a.area;
+            for (int k = threadIdx.x; k < kTileTris / 2; k += kThreads) cp_async16(&s_area[0][2 * k], src + 2 * k);
+            cp_async_commit();
+        }
+        for (int tile = 0; tile < a.nTiles; ++tile) {
+            if (tile + 1 < a.nTiles) {
+                const double* src = a.area + (size_t)(tile + 1) * kTileTris;
+                for (int k = threadIdx.x; k < kTileTris / 2; k += kThreads) cp_async16(&s_area[(tile + 1) & 1][2 * k], src + 2 * k);
+            }
+            cp_async_commit();
+            // ---- OR of the E rows for this tile ----
+            uint4 m = make_uint4(0, 0, 0, 0);
+            int vec = tile * (kTileWords / 4) + lane;  // uint4 index within the row
+            const bool inb = vec < rowVec;
+            if (act) {  // warp-uniform
+                for (int e0 = 0; e0 < nEdges; e0 += 32) {
+                    int myRow = rowOfEdge(e0 + lane);
+                    int cnt = min(32, nEdges - e0);
+                    int e = 0;
+                    for (; e + 4 <= cnt; e += 4) {
+                        int r0 = __shfl_sync(0xffffffffu, myRow, e), r1 = __shfl_sync(0xffffffffu, myRow, e + 1),
+                            r2 = __shfl_sync(0xffffffffu, myRow, e + 2), r3 = __shfl_sync(0xffffffffu, myRow, e + 3);
+                        uint4 z = make_uint4(0, 0, 0, 0);
+                        uint4 v0 = (inb && r0 >= 0) ? ldg_stream((const uint4*)(a.rows + (size_t)r0 * a.rowWords) + vec) : z;
+                        uint4 v1 = (inb && r1 >= 0) ? ldg_stream((const uint4*)(a.rows + (size_t)r1 * a.rowWords) + vec) : z;
+                        uint4 v2 = (inb && r2 >= 0) ? ldg_stream((const uint4*)(a.rows + (size_t)r2 * a.rowWords) + vec) : z;
+                        uint4 v3 = (inb && r3 >= 0) ? ldg_stream((const uint4*)(a.rows + (size_t)r3 * a.rowWords) + vec) : z;
+                        m.x |= v0.x | v1.x | v2.x | v3.x;
+                        m.y |= v0.y | v1.y | v2.y | v3.y;
+                        m.z |= v0.z | v1.z | v2.z | v3.z;
+                        m.w |= v0.w | v1.w | v2.w | v3.w;
+                    }
+                    for (; e < cnt; ++e) {
+                        int r = __shfl_sync(0xffffffffu, myRow, e);
+                        if (inb && r >= 0) {
+                            uint4 v = ldg_stream((const uint4*)(a.rows + (size_t)r * a.rowWords) + vec);
+                            m.x |= v.x; m.y |= v.y; m.z |= v.z; m.w |= v.w;
+                        }
+                    }
+                }
+            }
+            // ---- area tile of this step is ready ----
+            cp_async_wait<1>();
+            __syncthreads();
+            const double* ar = s_area[tile & 1];
+            unsigned nz = __ballot_sync(0xffffffffu, (m.x | m.y | m.z | m.w) != 0u);
+            while (nz) {
+                int q = __ffs(nz) - 1;
+                nz &= nz - 1;
+                unsigned w0 = __shfl_sync(0xffffffffu, m.x, q), w1 = __shfl_sync(0xffffffffu, m.y, q),
+                         w2 = __shfl_sync(0xffffffffu, m.z, q), w3 = __shfl_sync(0xffffffffu, m.w, q);
+                const double* base = ar + q * 128 + lane;
+                if ((w0 >> lane) & 1u) acc += base[0];
+                if ((w1 >> lane) & 1u) acc += base[32];
+                if ((w2 >> lane) & 1u) acc += base[64];
+                if ((w3 >> lane) & 1u) acc += base[96];
+            }
+            __syncthreads();  // everyone is done with this buffer before it is refilled two steps later
+        }
+        cp_async_wait<0>();
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (act && lane == 0) a.fitness[4 * p] = 1.0 - (acc / a.totalArea);
+    }
+}
+
+// OR of all rows whose key is marked used -> union bitmap (thread per word)
+__global__ void k_union_rows(const uint8_t* __restrict__ used, int nKeys, const int* __restrict__ rowmap, const uint32_t* __restrict__ rows,
+                             long long rowWords, uint32_t* __restrict__ out) {
+    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= rowWords) return;
+    uint32_t acc = 0;
+    for (int k = 0; k < nKeys; ++k) {
+        if (!used[k]) continue;
+        int r = rowmap[k];
+        if (r >= 0) acc |= rows[(size_t)r * rowWords + w];
+    }
+    out[w] = acc;
+}
+
+__global__ void k_fill_u8(uint8_t* p, long long n, uint8_t v) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_i32(int* p, long long n, int v) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_iota_i32(int* p, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int)(n - 1 - i);  // stack order: row 0 is popped first
+}
+__global__ void k_flush(uint32_t* p, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = (uint32_t)i;
+}
+
+}  // namespace
+
+void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st) {
+    if (a.pop <= 0) return;
+    static int perSM = 0;
+    if (!perSM) {
+        cudaFuncSetAttribute(k_plan_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaFuncSetAttribute(k_plan_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_plan_reduce, kThreads, kSmemBytes);
+        if (perSM < 1) perSM = 1;
+    }
+    long long groups = (a.pop + kPlansPerCta - 1) / kPlansPerCta;
+    int grid = (int)std::min<long long>((long long)numSMs * perSM, groups);
+    k_plan_reduce<<<grid, kThreads, kSmemBytes, st>>>(a);
+}
+
+void launch_union_rows(const uint8_t* d_used, int nKeys, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union,
+                       cudaStream_t st) {
+    k_union_rows<<<(unsigned)((rowWords + 127) / 128), 128, 0, st>>>(d_used, nKeys, d_rowmap, d_rows, (long long)rowWords, d_union);
+}
+void launch_fill_u8(uint8_t* p, int64_t n, uint8_t v, cudaStream_t st) {
+    if (n > 0) k_fill_u8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, (long long)n, v);
+}
+void launch_fill_i32(int* p, int64_t n, int v, cudaStream_t st) {
+    if (n > 0) k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, (long long)n, v);
+}
+void launch_iota_i32(int* p, int64_t n, cudaStream_t st) {
+    if (n > 0) k_iota_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, (long long)n);
+}
+void launch_flush(uint32_t* p, int64_t nWords, cudaStream_t st) {
+    if (nWords > 0) k_flush<<<148 * 8, 256, 0, st>>>(p, (long long)nWords);
+}
+
+}  // namespace ipp

@@ -385,6 +385,8 @@ struct Oracle {
     // canonical (lexicographically sorted) vertex order per triangle, used only
     // by the item buffer so that exact duplicate faces produce exact depth ties
     std::vector<V3f> cv;
+    // triangles whose fp64 normal (B-A)x(C-A) is exactly zero produce no fragments (GL: zero-area primitive)
+    std::vector<char> degenerate;
     // sensor (UF/CameraEstimator.cpp:53-63)
     double sampleInterval, fovY, aspect, zNear, zFar;
     unsigned imgH, imgW;
@@ -411,6 +413,7 @@ struct Oracle {
         if (T > (1u << 24)) throw std::logic_error("more than 256^3 primitives");  // UF/TriangleData.cpp:36
         area.resize(T);
         cv.resize(T * 3);
+        degenerate.assign(T, 0);
         bbmin = V3f{INFINITY, INFINITY, INFINITY};
         bbmax = V3f{-INFINITY, -INFINITY, -INFINITY};
         for (size_t i = 0; i < T; ++i) {
@@ -424,6 +427,10 @@ struct Oracle {
                 if (a.y != b.y) return a.y < b.y;
                 return a.z < b.z;
             });
+            {
+                V3 n = cross(widen(c[1]) - widen(c[0]), widen(c[2]) - widen(c[0]));
+                degenerate[i] = (n.x == 0 && n.y == 0 && n.z == 0);
+            }
             for (int k = 0; k < 3; ++k) {
                 cv[3 * i + k] = c[k];
                 const V3f& p = mesh.v[3 * i + k];
@@ -734,6 +741,7 @@ struct Oracle {
     }
     void setup_tri(const Cam& cam, size_t i, Setup& S) const {
         S.ok = false;
+        if (degenerate[i]) return;
         const V3 &s = cam.s, &u = cam.u, &f = cam.f;
         const int W = cam.W, H = cam.H;
         V3 A = widen(cv[3 * i]) - cam.eye, B = widen(cv[3 * i + 1]) - cam.eye, C = widen(cv[3 * i + 2]) - cam.eye;
