@@ -126,6 +126,9 @@ int ipp_render_ids(ipp_t* h, const double* eye3, const double* center3, const do
 /* BVH self-check: closest-hit of n rays (origin xyz, dir xyz) through the BVH and by brute force; returns
  * the number of mismatching ids */
 int ipp_bvh_selftest(ipp_t* h, const float* rays_nx6, int64_t n, int32_t* out_ids, int64_t* mismatches);
+/* same, also returning the brute-force ids and (t_bvh, t_brute) per ray */
+int ipp_bvh_selftest_ex(ipp_t* h, const float* rays_nx6, int64_t n, int32_t* out_ids, int32_t* out_brute_ids, float* out_t_nx2,
+                        int64_t* mismatches);
 
 /* ---- device memory, stream, timing (plumbing for bench.py) ---- */
 int ipp_device_alloc(ipp_t* h, int64_t bytes, void** out);

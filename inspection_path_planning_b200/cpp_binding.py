@@ -256,6 +256,16 @@ class PlanCoverageEstimator(object):
         _lib.check(self._L.ipp_bvh_selftest(self._h, r.ctypes.data_as(_lib.c_f32p), r.shape[0], ids.ctypes.data_as(_lib.c_i32p), C.byref(mism)))
         return ids, int(mism.value)
 
+    def bvh_selftest_ex(self, rays):
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
+        ids = np.zeros(r.shape[0], dtype=np.int32)
+        brute = np.zeros(r.shape[0], dtype=np.int32)
+        t = np.zeros((r.shape[0], 2), dtype=np.float32)
+        mism = C.c_int64()
+        _lib.check(self._L.ipp_bvh_selftest_ex(self._h, r.ctypes.data_as(_lib.c_f32p), r.shape[0], ids.ctypes.data_as(_lib.c_i32p),
+                                               brute.ctypes.data_as(_lib.c_i32p), t.ctypes.data_as(_lib.c_f32p), C.byref(mism)))
+        return ids, brute, t, int(mism.value)
+
     # ---- plumbing used by bench.py ----
     def sync(self):
         _lib.check(self._L.ipp_sync(self._h))

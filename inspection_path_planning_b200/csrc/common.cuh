@@ -30,6 +30,7 @@ constexpr double kEdgeSafetyBuffer = 1.5;
 constexpr double kCameraFarPlaneDist = 10.0;
 
 constexpr int kLeafMax = 4;          // triangles per BVH leaf
+constexpr int kMaxDepth = 96;        // Karras tree over 63-bit Morton codes + 31-bit index tie-break: depth <= 96
 constexpr int kTileWords = 128;      // bitmap words per plan_reduce tile (one uint4 per lane)
 constexpr int kTileTris = kTileWords * 32;
 
@@ -47,6 +48,7 @@ struct DeviceScene {
     int nNodes = 0;   // BVH nodes (root = 0)
     // BVH-ordered triangles, canonical (lexicographic) vertex order; a.w = original id as int bits
     float4 *ta = nullptr, *tb = nullptr, *tc = nullptr;
+    float4* tn = nullptr;  // geometric normal (B-A) x (C-A) of the canonical order, computed in fp64
     // BVH-ordered triangles, file vertex order (exact collision predicate); a.w = original id
     float4 *oa = nullptr, *ob = nullptr, *oc = nullptr;
     BvhNode* nodes = nullptr;

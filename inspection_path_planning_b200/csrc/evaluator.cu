@@ -621,25 +621,29 @@ void Evaluator::renderIds(const double* eye, const double* center, const double*
     cudaFree(d_img);
 }
 
-void Evaluator::bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches) {
+void Evaluator::bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute, float* outT) {
     bind();
     *mismatches = 0;
     if (n <= 0) return;
     float* d_r = dalloc<float>((size_t)n * 6);
     int32_t* d_a = dalloc<int32_t>(n);
     int32_t* d_b = dalloc<int32_t>(n);
+    float* d_t = outT ? dalloc<float>((size_t)n * 2) : nullptr;
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_r, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, stream_));
-    launch_bvh_selftest(scene_, d_r, n, d_a, d_b, stream_);
+    launch_bvh_selftest(scene_, d_r, n, d_a, d_b, d_t, stream_);
     nLaunches_++;
     std::vector<int32_t> b(n);
     IPP_CUDA_CHECK(cudaMemcpyAsync(outIds, d_a, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
     IPP_CUDA_CHECK(cudaMemcpyAsync(b.data(), d_b, (size_t)n * 4, cudaMemcpyDeviceToHost, stream_));
+    if (outT) IPP_CUDA_CHECK(cudaMemcpyAsync(outT, d_t, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
     sync();
     for (int64_t i = 0; i < n; ++i)
         if (outIds[i] != b[i]) (*mismatches)++;
+    if (outBrute) memcpy(outBrute, b.data(), (size_t)n * 4);
     cudaFree(d_r);
     cudaFree(d_a);
     cudaFree(d_b);
+    cudaFree(d_t);
 }
 
 }  // namespace ipp

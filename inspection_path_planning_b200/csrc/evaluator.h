@@ -42,7 +42,7 @@ class Evaluator {
     void edgesCollide(const double* edges, int64_t n, uint8_t* out);
     void boxesHitMesh(const double* centres, int64_t n, double half, uint8_t* out);
     void renderIds(const double* eye, const double* center, const double* up, int32_t* out);
-    void bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches);
+    void bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute = nullptr, float* outT = nullptr);
 
     // ---- plumbing ----
     void sync() { IPP_CUDA_CHECK(cudaStreamSynchronize(stream_)); }

@@ -72,7 +72,7 @@ __device__ __forceinline__ bool box_may_hit(const PlaneD pl[6], const double lo[
 
 __device__ bool polytope_hits_mesh(const DeviceScene& sc, const PlaneD pl[6], const double lo[3], const double hi[3]) {
     if (sc.T == 0) return false;
-    int stack[64];
+    int stack[kMaxDepth];
     int sp = 0;
     int node = 0;
     while (true) {
@@ -95,7 +95,7 @@ __device__ bool polytope_hits_mesh(const DeviceScene& sc, const PlaneD pl[6], co
                 }
             } else {
                 if (next < 0) next = link[c];
-                else if (sp < 64) stack[sp++] = link[c];
+                else if (sp < kMaxDepth) stack[sp++] = link[c];
             }
         }
         if (next >= 0) { node = next; continue; }

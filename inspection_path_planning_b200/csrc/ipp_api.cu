@@ -197,6 +197,12 @@ int ipp_bvh_selftest(ipp_t* h, const float* rays, int64_t n, int32_t* out_ids, i
     IPP_CATCH
 }
 
+int ipp_bvh_selftest_ex(ipp_t* h, const float* rays, int64_t n, int32_t* out_ids, int32_t* out_brute, float* out_t2, int64_t* mismatches) {
+    IPP_TRY
+    E(h).bvhSelftest(rays, n, out_ids, mismatches, out_brute, out_t2);
+    IPP_CATCH
+}
+
 int ipp_device_alloc(ipp_t* h, int64_t bytes, void** out) {
     IPP_TRY
     E(h).bind();

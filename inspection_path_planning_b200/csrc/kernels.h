@@ -81,7 +81,8 @@ void launch_visibility(const DeviceScene& sc, const CameraParams& cam, const Sna
                        unsigned long long* d_rayCounter, cudaStream_t st);
 // flags[slot][Tpad] (bytes) -> bitmap rows; clears the flags
 void launch_pack_rows(uint8_t* d_flags, int nSlots, int Tpad, const int* d_rowOfSlot, uint32_t* d_rows, int64_t rowWords, cudaStream_t st);
-void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, int32_t* d_idsBvh, int32_t* d_idsBrute, cudaStream_t st);
+void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, int32_t* d_idsBvh, int32_t* d_idsBrute, float* d_t /*nullable: (tBvh, tBrute) per ray*/,
+                         cudaStream_t st);
 int visibility_grid_blocks();
 size_t scan_tmp_bytes(int n);
 void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);

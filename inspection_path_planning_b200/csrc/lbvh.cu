@@ -135,7 +135,8 @@ __global__ void k_emit(int n, const int* __restrict__ left, const int* __restric
 }
 
 __global__ void k_gather(const float* __restrict__ verts, const float* __restrict__ canon, const uint8_t* __restrict__ degenerate,
-                         const int* __restrict__ vals, int n, float4* ta, float4* tb, float4* tc, float4* oa, float4* ob, float4* oc) {
+                         const int* __restrict__ vals, int n, float4* ta, float4* tb, float4* tc, float4* tn, float4* oa, float4* ob,
+                         float4* oc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int id = vals[i];
@@ -145,6 +146,11 @@ __global__ void k_gather(const float* __restrict__ verts, const float* __restric
     ta[i] = make_float4(c[0], c[1], c[2], idf);
     tb[i] = make_float4(c[3], c[4], c[5], degenerate[id] ? 1.f : 0.f);
     tc[i] = make_float4(c[6], c[7], c[8], 0.f);
+    // geometric normal (B-A) x (C-A) in fp64, rounded once: the depth of a hit is (A-eye).Ng / D.Ng, and an fp32 cross product
+    // of two nearly parallel edges (the long thin triangles of CAD meshes) would lose most of its digits
+    double e1x = (double)c[3] - c[0], e1y = (double)c[4] - c[1], e1z = (double)c[5] - c[2];
+    double e2x = (double)c[6] - c[0], e2y = (double)c[7] - c[1], e2z = (double)c[8] - c[2];
+    tn[i] = make_float4((float)(e1y * e2z - e1z * e2y), (float)(e1z * e2x - e1x * e2z), (float)(e1x * e2y - e1y * e2x), 0.f);
     oa[i] = make_float4(o[0], o[1], o[2], idf);
     ob[i] = make_float4(o[3], o[4], o[5], 0.f);
     oc[i] = make_float4(o[6], o[7], o[8], 0.f);
@@ -165,7 +171,7 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
     sc.T = T;
     sc.Tpad = (T + 31) / 32 * 32;
     for (int k = 0; k < 3; ++k) { sc.bbmin[k] = bbmin[k]; sc.bbmax[k] = bbmax[k]; }
-    sc.ta = dalloc<float4>(n); sc.tb = dalloc<float4>(n); sc.tc = dalloc<float4>(n);
+    sc.ta = dalloc<float4>(n); sc.tb = dalloc<float4>(n); sc.tc = dalloc<float4>(n); sc.tn = dalloc<float4>(n);
     sc.oa = dalloc<float4>(n); sc.ob = dalloc<float4>(n); sc.oc = dalloc<float4>(n);
     sc.nNodes = std::max(n - 1, 1);
     sc.nodes = dalloc<BvhNode>(sc.nNodes);
@@ -186,7 +192,7 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
     IPP_CUDA_CHECK(cudaMalloc(&tmp, std::max<size_t>(tmpBytes, 16)));
     cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keys2, vals, vals2, n, 0, 63, st);
 
-    k_gather<<<G, B, 0, st>>>(d_verts, d_canon, d_degenerate, vals2, n, sc.ta, sc.tb, sc.tc, sc.oa, sc.ob, sc.oc);
+    k_gather<<<G, B, 0, st>>>(d_verts, d_canon, d_degenerate, vals2, n, sc.ta, sc.tb, sc.tc, sc.tn, sc.oa, sc.ob, sc.oc);
 
     float4 *leafMin = dalloc<float4>(n), *leafMax = dalloc<float4>(n), *nodeMin = dalloc<float4>(n), *nodeMax = dalloc<float4>(n);
     int *left = dalloc<int>(n), *right = dalloc<int>(n), *rlo = dalloc<int>(n), *rhi = dalloc<int>(n), *parentI = dalloc<int>(n),
@@ -227,10 +233,10 @@ void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t 
 }
 
 void free_bvh(DeviceScene& sc) {
-    cudaFree(sc.ta); cudaFree(sc.tb); cudaFree(sc.tc);
+    cudaFree(sc.ta); cudaFree(sc.tb); cudaFree(sc.tc); cudaFree(sc.tn);
     cudaFree(sc.oa); cudaFree(sc.ob); cudaFree(sc.oc);
     cudaFree(sc.nodes);
-    sc.ta = sc.tb = sc.tc = sc.oa = sc.ob = sc.oc = nullptr;
+    sc.ta = sc.tb = sc.tc = sc.tn = sc.oa = sc.ob = sc.oc = nullptr;
     sc.nodes = nullptr;
 }
 

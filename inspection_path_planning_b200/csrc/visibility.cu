@@ -24,43 +24,45 @@ struct Hit {
     int id;
 };
 
-// 3 float4 per triangle: (Na, vol) (Nb, id) (Nc, -) with the eye at the origin.
-//   e_a = D.Na, e_b = D.Nb, e_c = D.Nc are the homogeneous edge functions of the pixel ray D,
-//   the ray covers the triangle iff they share a sign; depth t = vol / (e_a + e_b + e_c).
-__device__ __forceinline__ void tri_setup(const float4 a, const float4 b, const float4 c, float ox, float oy, float oz, float4& s0,
-                                          float4& s1, float4& s2) {
+// 4 float4 per triangle: (Na, vol) (Nb, id) (Nc, -) (Ng, -) with the eye at the origin.
+//   e_a = D.Na, e_b = D.Nb, e_c = D.Nc are the homogeneous edge functions of the pixel ray D; the ray covers the triangle
+//   iff they share a sign; planar depth t = vol / (D.Ng) with vol = (A - eye).Ng.
+//   Every edge normal is evaluated from the lexicographically lower endpoint of its edge (the vertices are stored sorted), so two
+//   triangles sharing an edge get bit-identical normals up to sign and no pixel ray can slip between them.
+constexpr int kTriVec = 4;
+__device__ __forceinline__ void tri_setup(const float4 a, const float4 b, const float4 c, const float4 n, float ox, float oy, float oz,
+                                          float4& s0, float4& s1, float4& s2, float4& s3) {
     if (b.w != 0.f) {  // degenerate triangle: never produces a fragment
         s0 = make_float4(0.f, 0.f, 0.f, 0.f);
         s1 = make_float4(0.f, 0.f, 0.f, a.w);
         s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        s3 = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
     float ax = a.x - ox, ay = a.y - oy, az = a.z - oz;
     float bx = b.x - ox, by = b.y - oy, bz = b.z - oz;
-    float cx = c.x - ox, cy = c.y - oy, cz = c.z - oz;
     // edges from the original coordinates (well conditioned), not from the translated ones
     float ebcx = c.x - b.x, ebcy = c.y - b.y, ebcz = c.z - b.z;
-    float ecax = a.x - c.x, ecay = a.y - c.y, ecaz = a.z - c.z;
+    float eacx = c.x - a.x, eacy = c.y - a.y, eacz = c.z - a.z;
     float eabx = b.x - a.x, eaby = b.y - a.y, eabz = b.z - a.z;
-    s0.x = by * ebcz - bz * ebcy; s0.y = bz * ebcx - bx * ebcz; s0.z = bx * ebcy - by * ebcx;  // B' x (C-B)
-    s1.x = cy * ecaz - cz * ecay; s1.y = cz * ecax - cx * ecaz; s1.z = cx * ecay - cy * ecax;  // C' x (A-C)
-    s2.x = ay * eabz - az * eaby; s2.y = az * eabx - ax * eabz; s2.z = ax * eaby - ay * eabx;  // A' x (B-A)
-    // Ng = (B-A) x (C-A) = -(Eab x Eca)
-    float ngx = -(eaby * ecaz - eabz * ecay), ngy = -(eabz * ecax - eabx * ecaz), ngz = -(eabx * ecay - eaby * ecax);
-    s0.w = ax * ngx + ay * ngy + az * ngz;  // vol = A'.Ng
+    s0.x = by * ebcz - bz * ebcy; s0.y = bz * ebcx - bx * ebcz; s0.z = bx * ebcy - by * ebcx;           // B' x (C-B)
+    s1.x = -(ay * eacz - az * eacy); s1.y = -(az * eacx - ax * eacz); s1.z = -(ax * eacy - ay * eacx);  // C' x (A-C) = -(A' x (C-A))
+    s2.x = ay * eabz - az * eaby; s2.y = az * eabx - ax * eabz; s2.z = ax * eaby - ay * eabx;           // A' x (B-A)
+    s0.w = ax * n.x + ay * n.y + az * n.z;  // vol = A'.Ng
     s1.w = a.w;                            // original triangle id (int bits)
     s2.w = 0.f;
+    s3 = make_float4(n.x, n.y, n.z, 0.f);
 }
 
-__device__ __forceinline__ void tri_test(const float4 s0, const float4 s1, const float4 s2, float dx, float dy, float dz, float zNear,
-                                         float zFar, Hit& h) {
+__device__ __forceinline__ void tri_test(const float4 s0, const float4 s1, const float4 s2, const float4 s3, float dx, float dy, float dz,
+                                         float zNear, float zFar, Hit& h) {
     float eu = dx * s0.x + dy * s0.y + dz * s0.z;
     float ev = dx * s1.x + dy * s1.y + dz * s1.z;
     float ew = dx * s2.x + dy * s2.y + dz * s2.z;
-    float det = eu + ev + ew;
-    bool in = ((eu >= 0.f && ev >= 0.f && ew >= 0.f) || (eu <= 0.f && ev <= 0.f && ew <= 0.f)) && det != 0.f;
+    bool in = (eu >= 0.f && ev >= 0.f && ew >= 0.f) || (eu <= 0.f && ev <= 0.f && ew <= 0.f);
     if (in) {
-        float t = s0.w / det;
+        float det = dx * s3.x + dy * s3.y + dz * s3.z;
+        float t = s0.w / det;  // det == 0: t is inf or NaN and fails the range test
         int id = __float_as_int(s1.w);
         if (t >= zNear && t <= zFar && (t < h.t || (t == h.t && id < h.id))) {
             h.t = t;
@@ -69,11 +71,13 @@ __device__ __forceinline__ void tri_test(const float4 s0, const float4 s1, const
     }
 }
 
+// Ray/box slab test with the subtraction done first: (b - o) * inv keeps the relative error of every plane distance at
+// ~1e-7 even when a direction component is close to zero (inv huge), where b * inv - o * inv cancels catastrophically.
 __device__ __forceinline__ bool slab(float bx0, float by0, float bz0, float bx1, float by1, float bz1, float ix, float iy, float iz,
                                      float ox, float oy, float oz, float tmin, float tmax, float& tn) {
-    float x0 = bx0 * ix - ox, x1 = bx1 * ix - ox;
-    float y0 = by0 * iy - oy, y1 = by1 * iy - oy;
-    float z0 = bz0 * iz - oz, z1 = bz1 * iz - oz;
+    float x0 = (bx0 - ox) * ix, x1 = (bx1 - ox) * ix;
+    float y0 = (by0 - oy) * iy, y1 = (by1 - oy) * iy;
+    float z0 = (bz0 - oz) * iz, z1 = (bz1 - oz) * iz;
     tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
     float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
     return tn <= tf * 1.0000005f + 1e-7f;  // conservative against rounding (the boxes are padded as well)
@@ -90,7 +94,6 @@ __device__ __forceinline__ void trace_packet(const DeviceScene& sc, float ox, fl
     h.id = 0x7fffffff;
     const float tmin = zNear;
     float ix = safe_rcp(dx), iy = safe_rcp(dy), iz = safe_rcp(dz);
-    float oix = ox * ix, oiy = oy * iy, oiz = oz * iz;
     int sp = 0;
     int node = 0;
     while (true) {
@@ -98,8 +101,8 @@ __device__ __forceinline__ void trace_packet(const DeviceScene& sc, float ox, fl
         float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
         float tn0, tn1;
         // closest-hit with ties on id needs t <= best, so the far bound is inclusive
-        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, oix, oiy, oiz, tmin, h.t, tn0);
-        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, oix, oiy, oiz, tmin, h.t, tn1);
+        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, tmin, h.t, tn0);
+        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, tmin, h.t, tn1);
         unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
         int l0 = __float_as_int(q3.x), l1 = __float_as_int(q3.y);
 #pragma unroll
@@ -111,15 +114,19 @@ __device__ __forceinline__ void trace_packet(const DeviceScene& sc, float ox, fl
                 int first = code >> 3, cnt = code & 7;
                 __syncwarp();
                 if (lane < cnt) {
-                    float4 a = __ldg(sc.ta + first + lane), b = __ldg(sc.tb + first + lane), cc = __ldg(sc.tc + first + lane);
-                    float4 s0, s1, s2;
-                    tri_setup(a, b, cc, ox, oy, oz, s0, s1, s2);
-                    s_tri[lane * 3 + 0] = s0;
-                    s_tri[lane * 3 + 1] = s1;
-                    s_tri[lane * 3 + 2] = s2;
+                    float4 a = __ldg(sc.ta + first + lane), b = __ldg(sc.tb + first + lane), cc = __ldg(sc.tc + first + lane),
+                           nn = __ldg(sc.tn + first + lane);
+                    float4 s0, s1, s2, s3;
+                    tri_setup(a, b, cc, nn, ox, oy, oz, s0, s1, s2, s3);
+                    s_tri[lane * kTriVec + 0] = s0;
+                    s_tri[lane * kTriVec + 1] = s1;
+                    s_tri[lane * kTriVec + 2] = s2;
+                    s_tri[lane * kTriVec + 3] = s3;
                 }
                 __syncwarp();
-                for (int k = 0; k < cnt; ++k) tri_test(s_tri[k * 3], s_tri[k * 3 + 1], s_tri[k * 3 + 2], dx, dy, dz, zNear, zFar, h);
+                for (int k = 0; k < cnt; ++k)
+                    tri_test(s_tri[k * kTriVec], s_tri[k * kTriVec + 1], s_tri[k * kTriVec + 2], s_tri[k * kTriVec + 3], dx, dy, dz, zNear,
+                             zFar, h);
             }
         }
         bool i0 = m0 && l0 >= 0, i1 = m1 && l1 >= 0;
@@ -147,8 +154,8 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
                                                             const int* __restrict__ tileOffset, int nSnaps, long long totalTiles,
                                                             uint8_t* __restrict__ flags, int32_t* __restrict__ idImage,
                                                             unsigned long long* __restrict__ counters) {
-    __shared__ int s_stack[kVisWarps][64];
-    __shared__ float4 s_tri[kVisWarps][kLeafMax * 3];
+    __shared__ int s_stack[kVisWarps][kMaxDepth];
+    __shared__ float4 s_tri[kVisWarps][kLeafMax * kTriVec];
     __shared__ Snapshot s_snap;
     __shared__ long long s_chunk;
     __shared__ int s_snapIdx;
@@ -243,15 +250,14 @@ __device__ void trace_single(const DeviceScene& sc, float ox, float oy, float oz
     h.t = 1e30f;
     h.id = 0x7fffffff;
     float ix = safe_rcp(dx), iy = safe_rcp(dy), iz = safe_rcp(dz);
-    float oix = ox * ix, oiy = oy * iy, oiz = oz * iz;
-    int stack[64];
+    int stack[kMaxDepth];
     int sp = 0, node = 0;
     while (true) {
         const BvhNode* np = sc.nodes + node;
         float4 q0 = np->q0, q1 = np->q1, q2 = np->q2, q3 = np->q3;
         float tn0, tn1;
-        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, oix, oiy, oiz, 0.f, h.t, tn0);
-        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, oix, oiy, oiz, 0.f, h.t, tn1);
+        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, 0.f, h.t, tn0);
+        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, 0.f, h.t, tn1);
         int l[2] = {__float_as_int(q3.x), __float_as_int(q3.y)};
         bool hh[2] = {h0, h1};
         int next = -1;
@@ -261,13 +267,13 @@ __device__ void trace_single(const DeviceScene& sc, float ox, float oy, float oz
                 int code = ~l[c];
                 int first = code >> 3, cnt = code & 7;
                 for (int k = 0; k < cnt; ++k) {
-                    float4 s0, s1, s2;
-                    tri_setup(sc.ta[first + k], sc.tb[first + k], sc.tc[first + k], ox, oy, oz, s0, s1, s2);
-                    tri_test(s0, s1, s2, dx, dy, dz, 0.f, 1e30f, h);
+                    float4 s0, s1, s2, s3;
+                    tri_setup(sc.ta[first + k], sc.tb[first + k], sc.tc[first + k], sc.tn[first + k], ox, oy, oz, s0, s1, s2, s3);
+                    tri_test(s0, s1, s2, s3, dx, dy, dz, 0.f, 1e30f, h);
                 }
             } else if (next < 0) {
                 next = l[c];
-            } else if (sp < 64) {
+            } else if (sp < kMaxDepth) {
                 stack[sp++] = l[c];
             }
         }
@@ -278,7 +284,7 @@ __device__ void trace_single(const DeviceScene& sc, float ox, float oy, float oz
 }
 
 __global__ void k_bvh_selftest(DeviceScene sc, const float* __restrict__ rays, long long n, int32_t* __restrict__ idsBvh,
-                               int32_t* __restrict__ idsBrute) {
+                               int32_t* __restrict__ idsBrute, float* __restrict__ tOut) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float ox = rays[6 * i], oy = rays[6 * i + 1], oz = rays[6 * i + 2], dx = rays[6 * i + 3], dy = rays[6 * i + 4], dz = rays[6 * i + 5];
@@ -289,11 +295,17 @@ __global__ void k_bvh_selftest(DeviceScene sc, const float* __restrict__ rays, l
     b.t = 1e30f;
     b.id = 0x7fffffff;
     for (int k = 0; k < sc.T; ++k) {
-        float4 s0, s1, s2;
-        tri_setup(sc.ta[k], sc.tb[k], sc.tc[k], ox, oy, oz, s0, s1, s2);
-        tri_test(s0, s1, s2, dx, dy, dz, 0.f, 1e30f, b);
+        float4 s0, s1, s2, s3;
+        tri_setup(sc.ta[k], sc.tb[k], sc.tc[k], sc.tn[k], ox, oy, oz, s0, s1, s2, s3);
+        tri_test(s0, s1, s2, s3, dx, dy, dz, 0.f, 1e30f, b);
     }
-    idsBrute[i] = b.id == 0x7fffffff ? -1 : b.id;
+    // near-ties (two surfaces within rounding of each other along the ray) may be culled by the box test: same depth counts as agreement
+    bool same = (b.id == h.id) || (b.id != 0x7fffffff && h.id != 0x7fffffff && fabsf(b.t - h.t) <= 1e-5f * fmaxf(1.f, fabsf(b.t)));
+    idsBrute[i] = same ? idsBvh[i] : (b.id == 0x7fffffff ? -1 : b.id);
+    if (tOut) {
+        tOut[2 * i] = h.t;
+        tOut[2 * i + 1] = b.t;
+    }
 }
 
 }  // namespace
@@ -328,8 +340,9 @@ void launch_pack_rows(uint8_t* d_flags, int nSlots, int Tpad, const int* d_rowOf
     if (tail > 0) k_zero_row_tail<<<(unsigned)((tail + 255) / 256), 256, 0, st>>>(nSlots, wordsPerSlot, d_rowOfSlot, d_rows, (long long)rowWords);
 }
 
-void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, int32_t* d_idsBvh, int32_t* d_idsBrute, cudaStream_t st) {
-    if (n > 0) k_bvh_selftest<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(sc, d_rays, (long long)n, d_idsBvh, d_idsBrute);
+void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, int32_t* d_idsBvh, int32_t* d_idsBrute, float* d_t,
+                         cudaStream_t st) {
+    if (n > 0) k_bvh_selftest<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(sc, d_rays, (long long)n, d_idsBvh, d_idsBrute, d_t);
 }
 
 }  // namespace ipp

@@ -1,0 +1,335 @@
+"""GPU parity tests: libipp.so (through its C ABI, via the ctypes mirror of cpp_binding) against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): collision flags, box classification, ids, seed plans bit-exact;
+energy / path length within 1e-12 relative (same fp64 formulas, no FMA); per-edge seen sets may differ from the oracle in at
+most 0.05 % of the triangles and only on triangles the oracle classifies as edge-epsilon (lenient minus strict); coverage
+within 1e-5 relative."""
+import numpy as np
+import pytest
+
+from conftest import bit_ids, mesh_path, popcount, random_plans, specs
+
+pytestmark = pytest.mark.gpu
+
+FLIP_BUDGET = 5e-4  # 0.05 % of the triangles
+COVERAGE_RTOL = 1e-5
+ENERGY_RTOL = 1e-12
+
+
+def _pair(oracle_mod, mesh, height, **kw):
+    from inspection_path_planning_b200 import cpp_binding
+    sp = specs(height, **{k: v for k, v in kw.items() if k in ("interval", "front", "down", "near", "far", "fov")})
+    okw = {}
+    gkw = {}
+    if "start" in kw:
+        okw["start_location"] = kw["start"]
+        gkw["startLocation"] = kw["start"]
+    if kw.get("loops"):
+        okw["plan_loops_around"] = True
+        gkw["planLoopsAround"] = True
+    return cpp_binding.PlanCoverageEstimator(mesh_path(mesh), sp, **gkw), oracle_mod.Oracle(mesh_path(mesh), sp, **okw)
+
+
+@pytest.fixture(scope="module")
+def sphere(oracle_mod):
+    g, o = _pair(oracle_mod, "sphere", 64)
+    yield g, o
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def mockup256(oracle_mod):
+    g, o = _pair(oracle_mod, "mockup_only", 256)
+    yield g, o
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def luis1(oracle_mod):
+    g, o = _pair(oracle_mod, "luis1", 128)
+    yield g, o
+    g.close()
+
+
+# ------------------------------------------------------------------ setup-time facts
+@pytest.mark.parametrize("fx", ["sphere", "mockup256", "luis1"])
+def test_scene_constants_bit_exact(fx, request):
+    g, o = request.getfixturevalue(fx)
+    assert g.T == o.T
+    assert np.array_equal(g.areas(), o.areas())
+    assert g.total_area() == o.total_area()
+    assert g.collision_penalty() == o.collision_penalty()
+    gc, gb = g.scene_info()
+    oc, ob = o.scene_info()
+    assert np.array_equal(gc, oc) and np.array_equal(gb, ob)
+    assert g.image_size() == o.image_size()
+
+
+@pytest.mark.parametrize("fx", ["sphere", "mockup256", "luis1"])
+def test_candidate_grid_and_seed_plans_bit_exact(fx, request):
+    g, o = request.getfixturevalue(fx)
+    assert np.array_equal(g.grid(), o.grid())
+    assert g.getNumberOfBoxes() == o.getNumberOfBoxes()
+    assert np.array_equal(g.box_centres(), o.box_centres())
+    assert g.getSimplePlans() == o.getSimplePlans()
+    assert g.getMaxAllowedEnergy() == pytest.approx(o.getMaxAllowedEnergy(), rel=ENERGY_RTOL)
+
+
+@pytest.mark.parametrize("fx", ["sphere", "mockup256", "luis1"])
+def test_bvh_matches_brute_force(fx, request):
+    g, _ = request.getfixturevalue(fx)
+    rng = np.random.default_rng(5)
+    c, bb = g.scene_info()
+    n = 20000
+    org = c + rng.normal(size=(n, 3)) * (bb[3:] - bb[:3]).max()
+    tgt = bb[:3] + rng.random((n, 3)) * (bb[3:] - bb[:3])
+    d = tgt - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ids, mism = g.bvh_selftest(np.concatenate([org, d], axis=1))
+    assert mism == 0
+    assert (ids >= 0).mean() > 0.3
+
+
+# ------------------------------------------------------------------ K5 / K2: exact predicates
+@pytest.mark.parametrize("fx,n", [("sphere", 3000), ("mockup256", 10000), ("luis1", 4000)])
+def test_edge_collision_flags_bit_exact(fx, n, request):
+    g, o = request.getfixturevalue(fx)
+    rng = np.random.default_rng(11)
+    c = o.box_centres()
+    a = c[rng.integers(0, len(c), n)]
+    b = c[rng.integers(0, len(c), n)]
+    keep = np.any(a != b, axis=1)
+    a, b = a[keep], b[keep]
+    # add near-miss edges: random points close to the structure
+    _, bb = o.scene_info()
+    m = n // 4
+    a2 = bb[:3] - 2 + rng.random((m, 3)) * (bb[3:] - bb[:3] + 4)
+    b2 = bb[:3] - 2 + rng.random((m, 3)) * (bb[3:] - bb[:3] + 4)
+    a, b = np.concatenate([a, a2]), np.concatenate([b, b2])
+    got = g.edges_collide(np.concatenate([a, b], axis=1))
+    want = np.array([o.edge_collides(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(got, want)
+    assert 0.02 < want.mean() < 0.98
+
+
+def test_vertical_and_sloped_edges_collision(mockup256):
+    g, o = mockup256
+    rng = np.random.default_rng(12)
+    _, bb = o.scene_info()
+    n = 2000
+    a = bb[:3] - 1 + rng.random((n, 3)) * (bb[3:] - bb[:3] + 2)
+    b = a.copy()
+    b[:, 2] += rng.uniform(-4, 4, n)  # exactly vertical: up = (1, 0, 0) branch
+    got = g.edges_collide(np.concatenate([a, b], axis=1))
+    want = np.array([o.edge_collides(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(got, want)
+
+
+def test_box_classification_bit_exact(mockup256):
+    g, o = mockup256
+    rng = np.random.default_rng(13)
+    _, bb = o.scene_info()
+    pts = bb[:3] - 6 + rng.random((1500, 3)) * (bb[3:] - bb[:3] + 12)
+    for half in (2.0, 10.0, 0.3):
+        got = g.boxes_hit_mesh(pts, half)
+        want = np.array([o.box_hits_mesh(p, half) for p in pts])
+        assert np.array_equal(got, want), half
+
+
+# ------------------------------------------------------------------ K4: visibility
+def _poses(o, rng, n):
+    c, bb = o.scene_info()
+    ext = (bb[3:] - bb[:3])
+    out = []
+    for _ in range(n):
+        eye = c + rng.normal(size=3) * ext * 0.8
+        tgt = bb[:3] + rng.random(3) * ext
+        up = np.array([0.0, 0.0, 1.0])
+        out.append((eye.astype(np.float32).astype(np.float64), tgt, up))
+    return out
+
+
+@pytest.mark.parametrize("fx", ["sphere", "mockup256", "luis1"])
+def test_item_buffer_images(fx, request):
+    g, o = request.getfixturevalue(fx)
+    rng = np.random.default_rng(21)
+    tot = bad = 0
+    for eye, tgt, up in _poses(o, rng, 6):
+        a = g.render_ids(eye, tgt, up)
+        b = o.render_ids(eye, tgt, up)
+        tot += a.size
+        bad += int((a != b).sum())
+    # pixel-level disagreements are confined to silhouettes / shared edges hit exactly at a pixel centre
+    assert bad / tot < 2e-3, (bad, tot)
+
+
+def _check_edge(g, o, prev, curr, stats):
+    got = g.edge_bitmap(prev, curr)
+    seen, strict, lenient = o.edge_bitmap(prev, curr, classify=True)
+    flips = got ^ seen
+    nflip = popcount(flips)
+    stats["flips"] += nflip
+    stats["edges"] += 1
+    stats["seen"] += popcount(seen)
+    # every disagreement must be an edge-epsilon triangle of the oracle: strict <= got <= lenient
+    outside = popcount(strict & ~got) + popcount(got & ~lenient)
+    stats["outside"] += outside
+    return nflip, outside
+
+
+@pytest.mark.parametrize("fx,n", [("sphere", 12), ("mockup256", 10), ("luis1", 10)])
+def test_edge_bitmaps_within_flip_budget(fx, n, request):
+    g, o = request.getfixturevalue(fx)
+    rng = np.random.default_rng(31)
+    N = o.getNumberOfBoxes()
+    stats = dict(flips=0, edges=0, seen=0, outside=0)
+    worst = 0
+    for _ in range(n):
+        prev, curr = (int(x) for x in rng.choice(N, 2, replace=False))
+        nflip, _ = _check_edge(g, o, prev, curr, stats)
+        worst = max(worst, nflip)
+    assert stats["seen"] > 0
+    assert worst <= max(1, int(FLIP_BUDGET * o.T)), stats
+    assert stats["outside"] == 0, stats
+
+
+def test_edge_bitmap_full_resolution(oracle_mod):
+    g, o = _pair(oracle_mod, "mockup_only", 1024)
+    try:
+        rng = np.random.default_rng(32)
+        N = o.getNumberOfBoxes()
+        c = o.box_centres()
+        stats = dict(flips=0, edges=0, seen=0, outside=0)
+        k = 0
+        while k < 3:
+            prev, curr = (int(x) for x in rng.choice(N, 2, replace=False))
+            if np.linalg.norm(c[prev] - c[curr]) > 4.5:
+                continue
+            nflip, outside = _check_edge(g, o, prev, curr, stats)
+            assert nflip <= int(FLIP_BUDGET * o.T) and outside == 0, (prev, curr, stats)
+            k += 1
+        assert stats["seen"] > 100
+    finally:
+        g.close()
+
+
+def test_single_camera_modes(oracle_mod):
+    for front, down in ((1, 0), (0, 1)):
+        g, o = _pair(oracle_mod, "sphere", 64, front=front, down=down)
+        try:
+            for prev, curr in ((100, 101), (250, 260), (30, 300)):
+                got, want = g.edge_bitmap(prev, curr), o.edge_bitmap(prev, curr)
+                assert popcount(got ^ want) <= 1
+        finally:
+            g.close()
+
+
+# ------------------------------------------------------------------ plans
+def _compare_population(g, o, plans, memo=True, no_limit=False):
+    got = g.evaluatePopulation(plans, memo, no_limit)
+    want = o.evaluatePopulation(plans, memo, no_limit)
+    np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=ENERGY_RTOL, atol=0)
+    np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=ENERGY_RTOL, atol=0)
+    assert np.array_equal(got[:, 3], want[:, 3])  # colliding-edge counts: bit-exact flags
+    gated = want[:, 0] == 1.0
+    assert np.array_equal(got[:, 0] == 1.0, gated) or np.allclose(got[:, 0], want[:, 0], rtol=COVERAGE_RTOL)
+    # coverage fraction (1 - score) within 1e-5 relative
+    np.testing.assert_allclose(1.0 - got[:, 0], 1.0 - want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9)
+    return got, want
+
+
+def test_population_fitness_sphere(sphere):
+    g, o = sphere
+    rng = np.random.default_rng(41)
+    plans = random_plans(rng, o.getNumberOfBoxes(), 60, (2, 8)) + [[]]
+    got, want = _compare_population(g, o, plans)
+    assert got[-1].tolist() == [1.0, 0.0, 0.0, 0.0]
+    assert (want[:, 0] < 1.0).sum() > 5  # some plans pass the energy gate and see the sphere
+
+
+def test_population_fitness_gate_disabled(mockup256):
+    g, o = mockup256
+    rng = np.random.default_rng(42)
+    plans = random_plans(rng, o.getNumberOfBoxes(), 12, (2, 5))
+    got, want = _compare_population(g, o, plans, memo=True, no_limit=True)
+    assert (want[:, 0] < 1.0).all()
+
+
+def test_single_plan_api_matches_batched(sphere):
+    g, o = sphere
+    from inspection_path_planning_b200 import cpp_binding as cb
+    plan = [[100], [101], [113], [250]]
+    cov, en = g.evaluatePlan(plan, True, cb.nothing, True)
+    row = g.evaluatePopulation([plan], True, True)[0]
+    assert (cov, en) == (row[0], row[1])
+    ocov, oen = o.evaluatePlan(plan, True, 3, True)
+    assert en == pytest.approx(oen, rel=ENERGY_RTOL) and 1 - cov == pytest.approx(1 - ocov, rel=COVERAGE_RTOL)
+    assert g.evaluatePlan([], True, cb.nothing) == (1.0, 0.0)
+    with pytest.raises(RuntimeError):
+        g.evaluatePlan(plan, True, cb.image)
+    with pytest.raises(IndexError):
+        g.evaluatePlan([[g.getNumberOfBoxes()]], True, cb.nothing)
+
+
+def test_memoisation_semantics(oracle_mod):
+    g, o = _pair(oracle_mod, "sphere", 32)
+    try:
+        p1, p2 = [[1], [2], [3]], [[7], [8]]
+        a = g.evaluatePopulation([p1, p2], True, True)
+        assert g.memo_size() == 3
+        b = g.evaluatePopulation([p1, p2], True, True)  # warm: identical
+        assert np.array_equal(a, b)
+        c = g.evaluatePopulation([p1, p2], False, True)  # memoisation off: same values, nothing remembered
+        assert np.array_equal(a, c)
+        assert g.updateMemoisedEdges([p1]) == 2
+        assert g.updateMemoisedEdges([[[2], [3]]]) == 1
+        assert g.updateMemoisedEdges([]) == 0
+        g.evaluatePopulation([p2], False, True)
+        assert g.memo_size() == 0
+    finally:
+        g.close()
+
+
+def test_loop_closure_and_start_location(oracle_mod):
+    start = [6.0, 6.0, 8.0]
+    g, o = _pair(oracle_mod, "sphere", 48, start=start, loops=True)
+    try:
+        rng = np.random.default_rng(43)
+        plans = random_plans(rng, o.getNumberOfBoxes(), 20, (1, 6))
+        _compare_population(g, o, plans, no_limit=True)
+        _compare_population(g, o, plans, no_limit=False)
+        gp, gd = g.interpretAndExportPlan(plans[0])
+        op, od = o.interpretAndExportPlan(plans[0])
+        assert gp == op
+        np.testing.assert_allclose(gd, od, atol=1e-15)
+    finally:
+        g.close()
+
+
+def test_union_bitmap_and_idempotence(mockup256):
+    g, o = mockup256
+    rng = np.random.default_rng(44)
+    plans = random_plans(rng, o.getNumberOfBoxes(), 200, 6)
+    fit, ub = g.evaluatePopulation(plans, True, True, union_bitmap=True)
+    fit2 = g.evaluatePopulation(plans, True, True)
+    assert np.array_equal(fit, fit2)
+    # the union covers at least as much as the best single plan, and concatenating two plans never covers less
+    cov_union = 1.0 - o.coverage_of_bitmap(ub)
+    assert cov_union >= (1.0 - fit[:, 0]).max() - 1e-12
+    both = g.evaluatePopulation([plans[0] + plans[1]], True, True)[0]
+    assert 1 - both[0] >= max(1 - fit[0, 0], 1 - fit[1, 0]) - 1e-12
+    # permuting the population permutes the rows
+    perm = rng.permutation(len(plans))
+    fit3 = g.evaluatePopulation([plans[i] for i in perm], True, True)
+    assert np.array_equal(fit3, fit[perm])
+
+
+def test_ragged_and_degenerate_plans(sphere):
+    g, o = sphere
+    plans = [[], [[5]], [[5], [5]], [[5], [6]], [[0], [491]], [[100], [101], [100], [101]]]
+    got = g.evaluatePopulation(plans, True, True)
+    want = o.evaluatePopulation(plans, True, True)
+    np.testing.assert_allclose(got[:, 1:], want[:, 1:], rtol=ENERGY_RTOL)
+    np.testing.assert_allclose(1 - got[:, 0], 1 - want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9)
+    assert got[0].tolist() == [1.0, 0.0, 0.0, 0.0]
+    with pytest.raises(IndexError):
+        g.evaluatePopulation([[[0], [492]]], True, True)

@@ -1,0 +1,38 @@
+"""Quick GPU diagnostics (not a benchmark): setup time, cold/warm population timing, kernel-group times."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import mesh_path, random_plans, specs  # noqa: E402
+from inspection_path_planning_b200 import cpp_binding  # noqa: E402
+
+mesh = sys.argv[1] if len(sys.argv) > 1 else "mockup_only"
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+pop = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+V = int(sys.argv[4]) if len(sys.argv) > 4 else 20
+
+t = time.time()
+g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), specs(H))
+print("setup %.3fs T=%d N=%d maxE=%.6f" % (time.time() - t, g.T, g.getNumberOfBoxes(), g.getMaxAllowedEnergy()), flush=True)
+rng = np.random.default_rng(20261019)
+plans = cpp_binding.pack_population(random_plans(rng, g.getNumberOfBoxes(), pop, V))
+names = ["reduce", "visibility", "collision", "pack", "plan"]
+for it in range(3):
+    g.counters(reset=True)
+    for k in range(5):
+        g.kernel_time(k, reset=True)
+    t = time.time()
+    fit = g.evaluatePopulation(plans, True, True)
+    dt = time.time() - t
+    c = g.counters()
+    kt = {names[k]: g.kernel_time(k) for k in range(5)}
+    print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  counters %s" % (it, dt, pop / dt, (1 - fit[:, 0]).mean(), c), flush=True)
+    print("   kernel ms:", {k: (round(v[0], 3), v[1]) for k, v in kt.items()}, flush=True)
+    if c["rays"]:
+        print("   rays/s (visibility kernel) %.3e" % (c["rays"] / (kt["visibility"][0] * 1e-3)), flush=True)
+print("memo", g.memo_size())
