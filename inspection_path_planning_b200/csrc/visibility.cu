@@ -18,6 +18,9 @@ namespace {
 constexpr int kVisWarps = 8;
 constexpr int kVisThreads = kVisWarps * 32;
 constexpr int kChunk = 8;  // macro tiles per scheduling step
+// Depth resolution of the item buffer (GL_LESS on a fixed-point depth buffer, triangles drawn in id order): fragments whose planar
+// depth is within a relative 2^-16 of the nearest one are ties and the lowest id keeps the pixel.  Same rule as the CPU oracle.
+constexpr float kDepthTie = 1.0f + 1.0f / 65536.0f;
 
 struct Hit {
     float t;
@@ -64,9 +67,10 @@ __device__ __forceinline__ void tri_test(const float4 s0, const float4 s1, const
         float det = dx * s3.x + dy * s3.y + dz * s3.z;
         float t = s0.w / det;  // det == 0: t is inf or NaN and fails the range test
         int id = __float_as_int(s1.w);
-        if (t >= zNear && t <= zFar && (t < h.t || (t == h.t && id < h.id))) {
-            h.t = t;
-            h.id = id;
+        // depth-tie band (kDepthTie): fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
+        if (t >= zNear && t <= zFar && t <= h.t * kDepthTie) {
+            h.id = (t * kDepthTie < h.t) ? id : min(h.id, id);  // clearly nearer: replace; inside the band: lowest id
+            h.t = fminf(h.t, t);
         }
     }
 }
@@ -100,9 +104,10 @@ __device__ __forceinline__ void trace_packet(const DeviceScene& sc, float ox, fl
         const BvhNode* np = sc.nodes + node;
         float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
         float tn0, tn1;
-        // closest-hit with ties on id needs t <= best, so the far bound is inclusive
-        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, tmin, h.t, tn0);
-        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, tmin, h.t, tn1);
+        // a fragment can still matter up to the end of the depth-tie band behind the nearest hit so far
+        const float tmax = h.t * kDepthTie;
+        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, tmin, tmax, tn0);
+        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, tmin, tmax, tn1);
         unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
         int l0 = __float_as_int(q3.x), l1 = __float_as_int(q3.y);
 #pragma unroll
@@ -256,8 +261,8 @@ __device__ void trace_single(const DeviceScene& sc, float ox, float oy, float oz
         const BvhNode* np = sc.nodes + node;
         float4 q0 = np->q0, q1 = np->q1, q2 = np->q2, q3 = np->q3;
         float tn0, tn1;
-        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, 0.f, h.t, tn0);
-        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, 0.f, h.t, tn1);
+        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, 0.f, h.t * kDepthTie, tn0);
+        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, 0.f, h.t * kDepthTie, tn1);
         int l[2] = {__float_as_int(q3.x), __float_as_int(q3.y)};
         bool hh[2] = {h0, h1};
         int next = -1;

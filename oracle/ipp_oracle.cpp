@@ -52,6 +52,14 @@ const double COLLISION_PENALTY_MODIFIER = 2.0;
 const double EDGE_SAFETY_BUFFER = 1.5;
 const double CAMERA_FAR_PLANE_DIST = 10;
 
+// Depth resolution of the item buffer.  The reference renders into a fixed-point GL depth buffer with depth
+// function LESS and submits the triangles in ID order (UF/TriangleData.cpp:93-106), so fragments whose depths
+// fall into the same depth-buffer step are ties and the first one drawn -- the lowest ID -- keeps the pixel.
+// Restated here as: among the fragments of a pixel whose planar depth is within a relative 2^-16 of the nearest
+// one, the lowest ID wins.  (Exactly coplanar, differently triangulated surfaces -- common in CAD exports such
+// as mockup_only.stl -- then resolve deterministically instead of by the rounding noise of the last bit.)
+const double DEPTH_TIE_REL = 1.0 / 65536.0;
+
 // ----------------------------------------------------------------------------
 // osg::Vec3d / osg::Vec3f arithmetic, restated (upstream OSG semantics, SURVEY
 // Appendix B): component-wise ops, dot = x*x' + y*y' + z*z' left to right,
@@ -811,19 +819,24 @@ struct Oracle {
         std::fill(zbuf.begin(), zbuf.begin() + NP, INFINITY);
         std::fill(idbuf.begin(), idbuf.begin() + NP, -1);
         Setup S;
-        for (size_t i = 0; i < T; ++i) {
-            setup_tri(cam, i, S);
-            if (!S.ok) continue;
-            for (int py = S.y0; py <= S.y1; ++py) {
-                double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
-                for (int px = S.x0; px <= S.x1; ++px) {
-                    double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
-                    double t;
-                    if (!frag(S, X, Y, t)) continue;
-                    size_t pix = (size_t)py * W + px;
-                    if (t >= zNear && t <= zFar && t < zbuf[pix]) {  // LESS, ascending ID => lower ID wins ties
-                        zbuf[pix] = t;
-                        idbuf[pix] = (int32_t)i;
+        // pass 1: nearest depth per pixel; pass 2: lowest ID within the depth-tie band of the nearest (see DEPTH_TIE_REL)
+        for (int pass = 0; pass < 2; ++pass) {
+            for (size_t i = 0; i < T; ++i) {
+                setup_tri(cam, i, S);
+                if (!S.ok) continue;
+                for (int py = S.y0; py <= S.y1; ++py) {
+                    double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
+                    for (int px = S.x0; px <= S.x1; ++px) {
+                        double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
+                        double t;
+                        if (!frag(S, X, Y, t)) continue;
+                        if (!(t >= zNear && t <= zFar)) continue;
+                        size_t pix = (size_t)py * W + px;
+                        if (pass == 0) {
+                            if (t < zbuf[pix]) zbuf[pix] = t;
+                        } else if (idbuf[pix] < 0 && t <= zbuf[pix] * (1.0 + DEPTH_TIE_REL)) {
+                            idbuf[pix] = (int32_t)i;  // ascending ID: the first one inside the band is the lowest
+                        }
                     }
                 }
             }
@@ -838,63 +851,44 @@ struct Oracle {
         const double offx[K] = {0, ex, ex, -ex, -ex}, offy[K] = {0, ey, -ey, ey, -ey};
         const double d = margins.eps_depth;
         const double lenLo = zNear * (1 - d), lenHi = zFar * (1 + d), strLo = zNear * (1 + d), strHi = zFar * (1 - d);
-        std::vector<double> z1(NP * K, INFINITY), z2(NP * K, INFINITY);
-        std::vector<int32_t> id1(NP * K, -1);
-        for (size_t i = 0; i < T; ++i) {
-            setup_tri(cam, i, S);
-            if (!S.ok) continue;
-            for (int py = S.y0; py <= S.y1; ++py) {
-                double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
-                for (int px = S.x0; px <= S.x1; ++px) {
-                    double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
-                    size_t pix = ((size_t)py * W + px) * K;
-                    for (int k = 0; k < K; ++k) {
-                        double t;
-                        if (!frag(S, X + offx[k], Y + offy[k], t)) continue;
-                        if (t < lenLo || t > lenHi) continue;
-                        if (t < z1[pix + k]) {
-                            z2[pix + k] = z1[pix + k];
-                            z1[pix + k] = t;
-                            id1[pix + k] = (int32_t)i;
-                        } else if (t < z2[pix + k]) {
-                            z2[pix + k] = t;
+        const double bandWide = (1.0 + DEPTH_TIE_REL) * (1 + d), bandNarrow = (1.0 + DEPTH_TIE_REL) * (1 - d);
+        // z1: nearest depth per sample position; idWide / idNarrow: lowest ID inside the widened / narrowed tie band
+        std::vector<double> z1(NP * K, INFINITY);
+        std::vector<int32_t> idWide(NP * K, -1), idNarrow(NP * K, -1);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (size_t i = 0; i < T; ++i) {
+                setup_tri(cam, i, S);
+                if (!S.ok) continue;
+                for (int py = S.y0; py <= S.y1; ++py) {
+                    double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
+                    for (int px = S.x0; px <= S.x1; ++px) {
+                        double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
+                        size_t pix = ((size_t)py * W + px) * K;
+                        for (int k = 0; k < K; ++k) {
+                            double t;
+                            if (!frag(S, X + offx[k], Y + offy[k], t)) continue;
+                            if (t < lenLo || t > lenHi) continue;
+                            if (pass == 0) {
+                                if (t < z1[pix + k]) z1[pix + k] = t;
+                            } else {
+                                if (idWide[pix + k] < 0 && t <= z1[pix + k] * bandWide) idWide[pix + k] = (int32_t)i;
+                                if (idNarrow[pix + k] < 0 && t <= z1[pix + k] * bandNarrow && t >= strLo && t <= strHi)
+                                    idNarrow[pix + k] = (int32_t)i;
+                                // lenient: inside the widened band of any sample position (ID competition ignored)
+                                if (t <= z1[pix + k] * bandWide) bits_set(*lenientSeen, i);
+                            }
                         }
                     }
                 }
             }
         }
+        // strict: the same triangle certainly owns the pixel at all five sample positions
         for (size_t p = 0; p < NP; ++p) {
-            int32_t id = id1[p * K];
+            int32_t id = idWide[p * K];
             if (id < 0) continue;
             bool ok = true;
-            for (int k = 0; k < K && ok; ++k) {
-                double t = z1[p * K + k];
-                ok = id1[p * K + k] == id && t >= strLo && t <= strHi && t * (1 + d) < z2[p * K + k];
-            }
+            for (int k = 0; k < K && ok; ++k) ok = idWide[p * K + k] == id && idNarrow[p * K + k] == id;
             if (ok) bits_set(*strictSeen, (size_t)id);
-        }
-        for (size_t i = 0; i < T; ++i) {
-            if (bits_get(*lenientSeen, i)) continue;
-            setup_tri(cam, i, S);
-            if (!S.ok) continue;
-            bool found = false;
-            for (int py = S.y0; py <= S.y1 && !found; ++py) {
-                double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
-                for (int px = S.x0; px <= S.x1 && !found; ++px) {
-                    double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
-                    size_t pix = ((size_t)py * W + px) * K;
-                    for (int k = 0; k < K; ++k) {
-                        double t;
-                        if (!frag(S, X + offx[k], Y + offy[k], t)) continue;
-                        if (t < lenLo || t > lenHi) continue;
-                        if (t <= z1[pix + k] * (1 + d)) {
-                            found = true;
-                            break;
-                        }
-                    }
-                }
-            }
-            if (found) bits_set(*lenientSeen, i);
         }
     }
 
