@@ -160,6 +160,12 @@ int ipp_comm_destroy(ipp_t* h);
  * fitness rows (one ncclAllGather over NVLink) so every rank holds all pop x 4. */
 int ipp_evaluate_population_sharded(ipp_t* h, const int32_t* ids, const float* angles, const int64_t* offsets,
                                     int64_t pop, int memoization, int disable_energy_limit, double* fitness_popx4);
+/* Device-resident form of the same step: this rank's `mine` plans (CSR on the device, offsets starting at 0) are
+ * evaluated into slot `rank` of d_fitness_all (world * per_rank rows of 4 doubles, device memory) and the slots are
+ * all-gathered in place.  Asynchronous on the evaluator's stream. */
+int ipp_evaluate_population_sharded_device(ipp_t* h, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets,
+                                           int64_t mine, int64_t n_genes, int64_t per_rank, int memoization,
+                                           int disable_energy_limit, double* d_fitness_all);
 int ipp_comm_barrier(ipp_t* h);
 int ipp_comm_allreduce_max(ipp_t* h, double* inout, int n);
 int ipp_comm_allreduce_sum(ipp_t* h, double* inout, int n);

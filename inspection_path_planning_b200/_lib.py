@@ -63,6 +63,8 @@ PROTOTYPES = {
     "ipp_comm_init": (C.c_int, [H, C.c_int, C.c_int, c_u8p]),
     "ipp_comm_destroy": (C.c_int, [H]),
     "ipp_evaluate_population_sharded": (C.c_int, [H, c_i32p, c_f32p, c_i64p, C.c_int64, C.c_int, C.c_int, c_f64p]),
+    "ipp_evaluate_population_sharded_device": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                                          C.c_int, C.c_void_p]),
     "ipp_comm_barrier": (C.c_int, [H]),
     "ipp_comm_allreduce_max": (C.c_int, [H, c_f64p, C.c_int]),
     "ipp_comm_allreduce_sum": (C.c_int, [H, c_f64p, C.c_int]),

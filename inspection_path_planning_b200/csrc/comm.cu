@@ -99,6 +99,20 @@ void comm_allreduce(Comm* c, double* inout, int n, int op, cudaStream_t st) {
     IPP_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+void comm_eval_device_and_allgather(Evaluator& ev, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t mine,
+                                    int64_t nGenes, int64_t per, bool memo, bool noLimit, double* d_gather) {
+    Comm* c = ev.comm_;
+    cudaStream_t st = ev.stream();
+    if (mine > per) throw std::invalid_argument("libipp: shard larger than the per-rank slot");
+    double* d_mine = d_gather + (size_t)c->rank * per * 4;
+    // rows of the last (short) shard that hold no plan are zero
+    if (mine < per) IPP_CUDA_CHECK(cudaMemsetAsync(d_mine + mine * 4, 0, (size_t)(per - mine) * 4 * sizeof(double), st));
+    // plan_reduce writes this rank's rows straight into its slot of the gather buffer: no staging copy before the collective
+    if (mine > 0) ev.evaluatePopulationDevice(d_ids, d_angles, d_offsets, mine, nGenes, memo, noLimit, d_mine, nullptr);
+    // the one exchange step: every rank receives every shard's fitness rows over NVLink
+    nccl_check(api().AllGather(d_mine, d_gather, (size_t)per * 4, ncclDouble, c->comm, st), "ncclAllGather");
+}
+
 void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, int64_t per,
                              int64_t lo, int64_t hi, bool memo, bool noLimit, double* fitness) {
     Comm* c = ev.comm_;
@@ -123,15 +137,11 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
     }
     std::vector<int64_t> off((size_t)mine + 1);
     for (int64_t i = 0; i <= mine; ++i) off[i] = offsets[lo + i] - g0;
-    double* d_mine = c->d_gather + (size_t)c->rank * per * 4;
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_mine, 0, (size_t)per * 4 * sizeof(double), st));
     if (mine > 0) {
         IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_ids, ids + g0, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_offsets, off.data(), (size_t)(mine + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        ev.evaluatePopulationDevice(c->d_ids, nullptr, c->d_offsets, mine, nGenes, memo, noLimit, d_mine, nullptr);
     }
-    // the one exchange step: every rank receives every shard's fitness rows over NVLink
-    nccl_check(api().AllGather(d_mine, c->d_gather, (size_t)per * 4, ncclDouble, c->comm, st), "ncclAllGather");
+    comm_eval_device_and_allgather(ev, c->d_ids, nullptr, c->d_offsets, mine, nGenes, per, memo, noLimit, c->d_gather);
     IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, c->d_gather, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     IPP_CUDA_CHECK(cudaStreamSynchronize(st));
 }

@@ -16,4 +16,8 @@ void comm_allreduce(Comm* c, double* inout, int n, int op, cudaStream_t st);
 // evaluate plans [lo, hi) of the population on this rank and all-gather `per` fitness rows per rank
 void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, int64_t per,
                              int64_t lo, int64_t hi, bool memo, bool noLimit, double* fitness);
+// device-resident form: this rank's `mine` plans (d_ids / d_offsets on the device) are evaluated into slot `rank` of
+// d_gather (world * per rows of 4 doubles) and the slots are all-gathered in place; asynchronous on the evaluator's stream
+void comm_eval_device_and_allgather(Evaluator& ev, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t mine,
+                                    int64_t nGenes, int64_t per, bool memo, bool noLimit, double* d_gather);
 }  // namespace ipp

@@ -308,6 +308,17 @@ int ipp_evaluate_population_sharded(ipp_t* h, const int32_t* ids, const float* a
     ipp::comm_eval_and_allgather(ev, ids, angles, offsets, pop, per, lo, hi, memoization != 0, disable_energy_limit != 0, fitness);
     IPP_CATCH
 }
+int ipp_evaluate_population_sharded_device(ipp_t* h, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t mine,
+                                           int64_t n_genes, int64_t per_rank, int memoization, int disable_energy_limit,
+                                           double* d_fitness_all) {
+    IPP_TRY
+    Evaluator& ev = E(h);
+    ev.bind();
+    if (!ev.comm_) throw std::logic_error("libipp: ipp_comm_init has not been called");
+    ipp::comm_eval_device_and_allgather(ev, d_ids, d_angles, d_offsets, mine, n_genes, per_rank, memoization != 0, disable_energy_limit != 0,
+                                        d_fitness_all);
+    IPP_CATCH
+}
 int ipp_comm_barrier(ipp_t* h) {
     IPP_TRY
     E(h).bind();

@@ -19,7 +19,7 @@ constexpr int kVisWarps = 8;
 constexpr int kVisThreads = kVisWarps * 32;
 constexpr int kChunk = 8;  // macro tiles per scheduling step
 // Depth resolution of the item buffer (GL_LESS on a fixed-point depth buffer, triangles drawn in id order): fragments whose planar
-// depth is within a relative 2^-16 of the nearest one are ties and the lowest id keeps the pixel.  Same rule as the CPU oracle.
+// depth is within a relative 2^-16 of the nearest one are ties and the lowest id keeps the pixel. 
 constexpr float kDepthTie = 1.0f + 1.0f / 65536.0f;
 
 struct Hit {
