@@ -29,7 +29,9 @@ constexpr double kCollisionPenaltyModifier = 2.0;
 constexpr double kEdgeSafetyBuffer = 1.5;
 constexpr double kCameraFarPlaneDist = 10.0;
 
-constexpr int kLeafMax = 4;          // triangles per BVH leaf
+constexpr int kLeafMax = 8;          // triangles per BVH leaf
+constexpr int kLeafShift = 4;        // leaf link: ~link = (first << kLeafShift) | count
+constexpr int kLeafMask = 15;
 constexpr int kMaxDepth = 96;        // Karras tree over 63-bit Morton codes + 31-bit index tie-break: depth <= 96
 constexpr int kTileWords = 128;      // bitmap words per plan_reduce tile (one uint4 per lane)
 constexpr int kTileTris = kTileWords * 32;
@@ -37,7 +39,7 @@ constexpr int kTileTris = kTileWords * 32;
 // One 64-byte BVH node: the boxes of both children and their links.
 //   q0 = (c0min.x, c0min.y, c0min.z, c0max.x)  q1 = (c0max.y, c0max.z, c1min.x, c1min.y)
 //   q2 = (c1min.z, c1max.x, c1max.y, c1max.z)  q3 = (link0, link1, -, -) as int bits
-// link >= 0: internal node index; link < 0: leaf, ~link = (first << 3) | count, count in 0..kLeafMax
+// link >= 0: internal node index; link < 0: leaf, ~link = (first << kLeafShift) | count, count in 0..kLeafMax
 struct BvhNode {
     float4 q0, q1, q2, q3;
 };

@@ -88,7 +88,7 @@ __device__ bool polytope_hits_mesh(const DeviceScene& sc, const PlaneD pl[6], co
             if (!hit[c]) continue;
             if (link[c] < 0) {
                 int code = ~link[c];
-                int first = code >> 3, cnt = code & 7;
+                int first = code >> kLeafShift, cnt = code & kLeafMask;
                 for (int k = 0; k < cnt; ++k) {
                     float4 a = __ldg(sc.oa + first + k), b = __ldg(sc.ob + first + k), cc = __ldg(sc.oc + first + k);
                     if (polytope_hits_triangle(pl, d3(a.x, a.y, a.z), d3(b.x, b.y, b.z), d3(cc.x, cc.y, cc.z))) return true;

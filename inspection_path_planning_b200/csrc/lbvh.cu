@@ -114,12 +114,12 @@ __global__ void k_emit(int n, const int* __restrict__ left, const int* __restric
         int L = ch[c];
         if (L < 0) {
             int idx = L & 0x7fffffff;
-            link[c] = ~((idx << 3) | 1);
+            link[c] = ~((idx << kLeafShift) | 1);
             mn[c] = leafMin[idx];
             mx[c] = leafMax[idx];
         } else {
             int cnt = rhi[L] - rlo[L] + 1;
-            link[c] = (cnt <= kLeafMax) ? ~((rlo[L] << 3) | cnt) : L;
+            link[c] = (cnt <= kLeafMax) ? ~((rlo[L] << kLeafShift) | cnt) : L;
             mn[c] = nodeMin[L];
             mx[c] = nodeMax[L];
         }
@@ -209,7 +209,7 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
         nd.q0 = make_float4(bbmin[0] - pad, bbmin[1] - pad, bbmin[2] - pad, bbmax[0] + pad);
         nd.q1 = make_float4(bbmax[1] + pad, bbmax[2] + pad, 1e30f, 1e30f);
         nd.q2 = make_float4(1e30f, -1e30f, -1e30f, -1e30f);
-        int l0 = ~((0 << 3) | 1), l1 = ~0;
+        int l0 = ~((0 << kLeafShift) | 1), l1 = ~0;
         float f0, f1;
         memcpy(&f0, &l0, 4);
         memcpy(&f1, &l1, 4);

@@ -2,76 +2,80 @@
 // (viewer.frame() + glReadPixels + getAllColorsInFrame; ImageViewerCaptureTool.cpp:59-70,
 // CameraEstimator.cpp:99-129,131-178).
 //
-// Per camera pose: the scene box is culled against the camera frustum into a rectangle of 32x32-pixel
-// macro tiles (exact.cu); one CTA takes a macro tile, each warp an 8x4-pixel packet; the 32 pixel-centre
-// rays of a packet walk the BVH together with one warp-uniform stack in shared memory (ballot-voted
-// child order, leaves of <= 4 triangles set up once by <= 4 lanes into shared memory and tested by all
-// 32 rays).  The nearest triangle inside planar depth [zNear, zFar] (ties: lower id, = GL_LESS in
-// draw order) gets its byte flag set with a plain store -- no atomics; k_pack_rows then builds the
-// bitmap words with byte->bit multiplies and clears the flags.
+// Tile-packet ray casting.  Per camera pose the scene box is culled against the camera frustum into a rectangle of
+// 32x32-pixel tiles (exact.cu).  One warp takes one tile: its 1024 pixel-centre rays walk the BVH together as one frustum
+// packet -- the warp tests both child boxes of a node against the four side planes of the tile frustum, the near plane and
+// the tile's current farthest hit (12 plane tests spread over 12 lanes, one ballot), front child first, on a warp-uniform
+// stack in shared memory.  At a leaf up to 8 lanes set up one triangle each into shared memory (homogeneous edge functions
+// of the pixel ray D = f + X s + Y u: e(X, Y) = N.f + (N.s) X + (N.u) Y, depth t = (A - eye).Ng / D.Ng, projected bounding
+// rectangle); the warp then runs the ray/triangle test for the rays inside that rectangle, 8x4 pixels per step, every lane
+// owning the same 32 pixels of the tile throughout, and keeps the nearest hit per ray in shared memory: no atomics.
+// The nearest triangle inside planar depth [zNear, zFar] gets its byte flag set with a plain store; k_pack_rows then builds
+// the bitmap words with byte->bit multiplies and clears the flags.
+//
+// Numerics that matter for parity:
+//  * every edge normal is evaluated from the lexicographically lower endpoint of its edge (vertices are stored sorted), so two
+//    triangles sharing an edge get bit-identical coefficients up to sign and no pixel ray slips between them;
+//  * Ng comes from an fp64 cross product (lbvh.cu), the fp32 one loses most digits on long thin triangles;
+//  * depth resolution: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins (GL_LESS on a
+//    fixed-point depth buffer, triangles drawn in id order).
 #include "kernels.h"
 
 namespace ipp {
 
 namespace {
 
-constexpr int kVisWarps = 8;
+constexpr int kVisWarps = 4;
 constexpr int kVisThreads = kVisWarps * 32;
-constexpr int kChunk = 8;  // macro tiles per scheduling step
-// Depth resolution of the item buffer (GL_LESS on a fixed-point depth buffer, triangles drawn in id order): fragments whose planar
-// depth is within a relative 2^-16 of the nearest one are ties and the lowest id keeps the pixel. 
+constexpr int kGrab = 4;        // tiles a warp claims per scheduling step
+constexpr int kTile = 32;       // tile side in pixels
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kNoId = 0x7fffffff;
 constexpr float kDepthTie = 1.0f + 1.0f / 65536.0f;
+constexpr int kTriWords = 16;   // floats per staged triangle
 
 struct Hit {
     float t;
     int id;
 };
 
-// 4 float4 per triangle: (Na, vol) (Nb, id) (Nc, -) (Ng, -) with the eye at the origin.
-//   e_a = D.Na, e_b = D.Nb, e_c = D.Nc are the homogeneous edge functions of the pixel ray D; the ray covers the triangle
-//   iff they share a sign; planar depth t = vol / (D.Ng) with vol = (A - eye).Ng.
-//   Every edge normal is evaluated from the lexicographically lower endpoint of its edge (the vertices are stored sorted), so two
-//   triangles sharing an edge get bit-identical normals up to sign and no pixel ray can slip between them.
-constexpr int kTriVec = 4;
-__device__ __forceinline__ void tri_setup(const float4 a, const float4 b, const float4 c, const float4 n, float ox, float oy, float oz,
-                                          float4& s0, float4& s1, float4& s2, float4& s3) {
-    if (b.w != 0.f) {  // degenerate triangle: never produces a fragment
-        s0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        s1 = make_float4(0.f, 0.f, 0.f, a.w);
-        s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        s3 = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
+// Edge normals with the eye at the origin.  e_a = D.Na, e_b = D.Nb, e_c = D.Nc are the homogeneous edge functions of a ray D.
+__device__ __forceinline__ void edge_normals(const float4 a, const float4 b, const float4 c, float ox, float oy, float oz, float3& na,
+                                             float3& nb, float3& nc, float3& ap) {
     float ax = a.x - ox, ay = a.y - oy, az = a.z - oz;
     float bx = b.x - ox, by = b.y - oy, bz = b.z - oz;
     // edges from the original coordinates (well conditioned), not from the translated ones
     float ebcx = c.x - b.x, ebcy = c.y - b.y, ebcz = c.z - b.z;
     float eacx = c.x - a.x, eacy = c.y - a.y, eacz = c.z - a.z;
     float eabx = b.x - a.x, eaby = b.y - a.y, eabz = b.z - a.z;
-    s0.x = by * ebcz - bz * ebcy; s0.y = bz * ebcx - bx * ebcz; s0.z = bx * ebcy - by * ebcx;           // B' x (C-B)
-    s1.x = -(ay * eacz - az * eacy); s1.y = -(az * eacx - ax * eacz); s1.z = -(ax * eacy - ay * eacx);  // C' x (A-C) = -(A' x (C-A))
-    s2.x = ay * eabz - az * eaby; s2.y = az * eabx - ax * eabz; s2.z = ax * eaby - ay * eabx;           // A' x (B-A)
-    s0.w = ax * n.x + ay * n.y + az * n.z;  // vol = A'.Ng
-    s1.w = a.w;                            // original triangle id (int bits)
-    s2.w = 0.f;
-    s3 = make_float4(n.x, n.y, n.z, 0.f);
+    na = make_float3(by * ebcz - bz * ebcy, bz * ebcx - bx * ebcz, bx * ebcy - by * ebcx);           // B' x (C-B)
+    nb = make_float3(-(ay * eacz - az * eacy), -(az * eacx - ax * eacz), -(ax * eacy - ay * eacx));  // C' x (A-C) = -(A' x (C-A))
+    nc = make_float3(ay * eabz - az * eaby, az * eabx - ax * eabz, ax * eaby - ay * eabx);           // A' x (B-A)
+    ap = make_float3(ax, ay, az);
 }
 
-__device__ __forceinline__ void tri_test(const float4 s0, const float4 s1, const float4 s2, const float4 s3, float dx, float dy, float dz,
-                                         float zNear, float zFar, Hit& h) {
-    float eu = dx * s0.x + dy * s0.y + dz * s0.z;
-    float ev = dx * s1.x + dy * s1.y + dz * s1.z;
-    float ew = dx * s2.x + dy * s2.y + dz * s2.z;
+__device__ __forceinline__ void depth_update(float t, int id, float zNear, float zFar, Hit& h) {
+    // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
+    if (t >= zNear && t <= zFar && t <= h.t * kDepthTie) {
+        h.id = (t * kDepthTie < h.t) ? id : min(h.id, id);  // clearly nearer: replace; inside the band: lowest id
+        h.t = fminf(h.t, t);
+    }
+}
+
+// ray form of the test, used by the BVH self test
+__device__ __forceinline__ void ray_tri_test(const float4 a, const float4 b, const float4 c, const float4 n, float ox, float oy, float oz,
+                                             float dx, float dy, float dz, float zNear, float zFar, Hit& h) {
+    if (b.w != 0.f) return;  // degenerate triangle: never produces a fragment
+    float3 na, nb, nc, ap;
+    edge_normals(a, b, c, ox, oy, oz, na, nb, nc, ap);
+    float eu = dx * na.x + dy * na.y + dz * na.z;
+    float ev = dx * nb.x + dy * nb.y + dz * nb.z;
+    float ew = dx * nc.x + dy * nc.y + dz * nc.z;
     bool in = (eu >= 0.f && ev >= 0.f && ew >= 0.f) || (eu <= 0.f && ev <= 0.f && ew <= 0.f);
     if (in) {
-        float det = dx * s3.x + dy * s3.y + dz * s3.z;
-        float t = s0.w / det;  // det == 0: t is inf or NaN and fails the range test
-        int id = __float_as_int(s1.w);
-        // depth-tie band (kDepthTie): fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
-        if (t >= zNear && t <= zFar && t <= h.t * kDepthTie) {
-            h.id = (t * kDepthTie < h.t) ? id : min(h.id, id);  // clearly nearer: replace; inside the band: lowest id
-            h.t = fminf(h.t, t);
-        }
+        float det = dx * n.x + dy * n.y + dz * n.z;
+        float vol = ap.x * n.x + ap.y * n.y + ap.z * n.z;
+        depth_update(vol / det, __float_as_int(a.w), zNear, zFar, h);  // det == 0: inf / NaN fails the range test
     }
 }
 
@@ -87,138 +91,269 @@ __device__ __forceinline__ bool slab(float bx0, float by0, float bz0, float bx1,
     return tn <= tf * 1.0000005f + 1e-7f;  // conservative against rounding (the boxes are padded as well)
 }
 
-__device__ __forceinline__ float safe_rcp(float d) {
-    return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d));
-}
+__device__ __forceinline__ float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
 
-// Warp-cooperative closest-hit traversal: all 32 rays share the origin and one stack.
-__device__ __forceinline__ void trace_packet(const DeviceScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, bool valid,
-                                             float zNear, float zFar, int* stack, float4* s_tri, int lane, Hit& h) {
-    h.t = valid ? zFar : -1.f;  // an invalid lane has an empty interval
-    h.id = 0x7fffffff;
-    const float tmin = zNear;
-    float ix = safe_rcp(dx), iy = safe_rcp(dy), iz = safe_rcp(dz);
-    int sp = 0;
-    int node = 0;
-    while (true) {
-        const BvhNode* np = sc.nodes + node;
-        float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
-        float tn0, tn1;
-        // a fragment can still matter up to the end of the depth-tie band behind the nearest hit so far
-        const float tmax = h.t * kDepthTie;
-        bool h0 = slab(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ix, iy, iz, ox, oy, oz, tmin, tmax, tn0);
-        bool h1 = slab(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ix, iy, iz, ox, oy, oz, tmin, tmax, tn1);
-        unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-        int l0 = __float_as_int(q3.x), l1 = __float_as_int(q3.y);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            unsigned m = c ? m1 : m0;
-            int l = c ? l1 : l0;
-            if (m && l < 0) {
-                int code = ~l;
-                int first = code >> 3, cnt = code & 7;
-                __syncwarp();
-                if (lane < cnt) {
-                    float4 a = __ldg(sc.ta + first + lane), b = __ldg(sc.tb + first + lane), cc = __ldg(sc.tc + first + lane),
-                           nn = __ldg(sc.tn + first + lane);
-                    float4 s0, s1, s2, s3;
-                    tri_setup(a, b, cc, nn, ox, oy, oz, s0, s1, s2, s3);
-                    s_tri[lane * kTriVec + 0] = s0;
-                    s_tri[lane * kTriVec + 1] = s1;
-                    s_tri[lane * kTriVec + 2] = s2;
-                    s_tri[lane * kTriVec + 3] = s3;
-                }
-                __syncwarp();
-                for (int k = 0; k < cnt; ++k)
-                    tri_test(s_tri[k * kTriVec], s_tri[k * kTriVec + 1], s_tri[k * kTriVec + 2], s_tri[k * kTriVec + 3], dx, dy, dz, zNear,
-                             zFar, h);
-            }
-        }
-        bool i0 = m0 && l0 >= 0, i1 = m1 && l1 >= 0;
-        if (i0 && i1) {
-            // visit first the child that more rays enter first
-            int v1 = __popc(__ballot_sync(0xffffffffu, h1 && (!h0 || tn1 < tn0)));
-            int v0 = __popc(__ballot_sync(0xffffffffu, h0 && (!h1 || tn0 <= tn1)));
-            int nearL = (v1 > v0) ? l1 : l0, farL = (v1 > v0) ? l0 : l1;
-            if (lane == 0) stack[sp] = farL;
-            sp++;
-            node = nearL;
-        } else if (i0) {
-            node = l0;
-        } else if (i1) {
-            node = l1;
-        } else {
-            if (sp == 0) break;
-            __syncwarp();
-            node = stack[--sp];
-        }
+// ------------------------------------------------------------------------------------------------------------------
+// K4
+// ------------------------------------------------------------------------------------------------------------------
+struct WarpShared {
+    float t[kTilePixels];            // nearest depth per ray, index = block * 32 + lane (block = 8x4 pixels)
+    int id[kTilePixels];             // its triangle
+    float tri[kLeafMax][kTriWords];  // staged leaf triangles
+    int stack[2 * kMaxDepth];        // (link, zmin bits) pairs
+};
+
+// last index s in [0, nSnaps) with tileOffset[s] <= task (tileOffset[0] == 0): 32-ary search, one probe per lane and round
+__device__ __forceinline__ int find_snapshot(const int* __restrict__ tileOffset, int nSnaps, long long task, int lane) {
+    int lo = 0, hi = nSnaps - 1;
+    while (hi > lo) {
+        int span = hi - lo;
+        int step = (span + 31) >> 5;
+        int pos = min(hi, lo + (lane + 1) * step);
+        bool le = (long long)__ldg(tileOffset + pos) <= task;
+        int k = __popc(__ballot_sync(0xffffffffu, le));
+        int nlo = k ? min(hi, lo + k * step) : lo;
+        int nhi = (k < 32) ? min(hi, lo + (k + 1) * step) - 1 : hi;
+        lo = nlo;
+        hi = max(nhi, nlo);
     }
+    return lo;
 }
 
 __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
                                                             const int* __restrict__ tileOffset, int nSnaps, long long totalTiles,
                                                             uint8_t* __restrict__ flags, int32_t* __restrict__ idImage,
                                                             unsigned long long* __restrict__ counters) {
-    __shared__ int s_stack[kVisWarps][kMaxDepth];
-    __shared__ float4 s_tri[kVisWarps][kLeafMax * kTriVec];
-    __shared__ Snapshot s_snap;
-    __shared__ long long s_chunk;
-    __shared__ int s_snapIdx;
+    __shared__ WarpShared s_all[kVisWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpShared& S = s_all[warp];
     unsigned long long myRays = 0;
+    // pixel-centre image-plane coordinates: X(px) = ((px + 0.5) / W * 2 - 1) tanX = px kx + cx
+    const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
+    const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
+    const float ikx = 1.0f / kx, iky = 1.0f / ky;
+    const float zNear = cam.zNear, zFar = cam.zFar;
+    // this lane's role in the node test: child = lane / 6, quantity = lane % 6 (lanes >= 12 idle)
+    const int role = lane < 12 ? lane % 6 : 0;
+    const bool second = lane >= 6 && lane < 12;
+
     while (true) {
-        if (threadIdx.x == 0) s_chunk = (long long)atomicAdd(&counters[1], (unsigned long long)kChunk);
-        __syncthreads();
-        long long c0 = s_chunk;
-        if (c0 >= totalTiles) break;
-        long long c1 = c0 + kChunk < totalTiles ? c0 + kChunk : totalTiles;
-        if (threadIdx.x == 0) {
-            // last snapshot whose first tile is <= c0 (tileOffset has nSnaps + 1 entries)
-            int lo = 0, hi = nSnaps - 1;
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if ((long long)tileOffset[mid] <= c0) lo = mid; else hi = mid - 1;
-            }
-            s_snapIdx = lo;
-        }
-        __syncthreads();
-        int si = s_snapIdx;
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(&counters[1], (unsigned long long)kGrab);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= totalTiles) break;
+        const long long end = base + kGrab < totalTiles ? base + kGrab : totalTiles;
+        int si = find_snapshot(tileOffset, nSnaps, base, lane);
         int loaded = -1;
-        for (long long task = c0; task < c1; ++task) {
-            while ((long long)tileOffset[si + 1] <= task) si++;  // skips culled (empty) snapshots
+        float ox = 0, oy = 0, oz = 0, fx = 0, fy = 0, fz = 0, sx = 0, sy = 0, sz = 0, ux = 0, uy = 0, uz = 0;
+        int slot = 0, rx0 = 0, ry0 = 0, rnx = 1;
+        for (long long task = base; task < end; ++task) {
+            while ((long long)__ldg(tileOffset + si + 1) <= task) si++;  // skips culled (empty) snapshots
             if (si != loaded) {
-                __syncthreads();
-                const int* src = (const int*)(snaps + si);
-                int* dst = (int*)&s_snap;
-                for (int k = threadIdx.x; k < (int)(sizeof(Snapshot) / 4); k += kVisThreads) dst[k] = src[k];
+                const Snapshot* sp = snaps + si;
+                fx = (float)sp->f[0]; fy = (float)sp->f[1]; fz = (float)sp->f[2];
+                sx = (float)sp->s[0]; sy = (float)sp->s[1]; sz = (float)sp->s[2];
+                ux = (float)sp->u[0]; uy = (float)sp->u[1]; uz = (float)sp->u[2];
+                ox = sp->eye[0]; oy = sp->eye[1]; oz = sp->eye[2];
+                slot = sp->slot; rx0 = sp->rx0; ry0 = sp->ry0; rnx = sp->rnx;
                 loaded = si;
-                __syncthreads();
             }
-            int local = (int)(task - tileOffset[si]);
-            int mx = s_snap.rx0 + local % s_snap.rnx, my = s_snap.ry0 + local / s_snap.rnx;
-            float ox = s_snap.eye[0], oy = s_snap.eye[1], oz = s_snap.eye[2];
-            for (int sub = warp; sub < 32; sub += kVisWarps) {
-                int px = mx * 32 + (sub & 3) * 8 + (lane & 7);
-                int py = my * 32 + (sub >> 2) * 4 + (lane >> 3);
-                bool valid = px < cam.W && py < cam.H;
-                // pixel centre in image-plane units; the ray is scaled so that t is the planar depth (D.f = 1)
-                double X = ((px + 0.5) / cam.W * 2.0 - 1.0) * cam.tanX;
-                double Y = ((py + 0.5) / cam.H * 2.0 - 1.0) * cam.tanY;
-                float dx = (float)(s_snap.f[0] + s_snap.s[0] * X + s_snap.u[0] * Y);
-                float dy = (float)(s_snap.f[1] + s_snap.s[1] * X + s_snap.u[1] * Y);
-                float dz = (float)(s_snap.f[2] + s_snap.s[2] * X + s_snap.u[2] * Y);
-                Hit h;
-                trace_packet(sc, ox, oy, oz, dx, dy, dz, valid, cam.zNear, cam.zFar, s_stack[warp], s_tri[warp], lane, h);
-                bool hit = valid && h.id != 0x7fffffff;
-                if (hit) flags[(size_t)s_snap.slot * sc.Tpad + h.id] = 1;
-                if (idImage && valid) idImage[(size_t)py * cam.W + px] = hit ? h.id : -1;
-                if (valid) myRays++;
+            const int local = (int)(task - __ldg(tileOffset + si));
+            const int tpx0 = (rx0 + local % rnx) * kTile, tpy0 = (ry0 + local / rnx) * kTile;
+            // ---- tile state ----
+#pragma unroll
+            for (int k = 0; k < kTilePixels / 32; ++k) {
+                S.t[k * 32 + lane] = zFar;
+                S.id[k * 32 + lane] = kNoId;
             }
+            const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
+            int nEmpty = vw * vh;            // rays without a hit yet (warp-uniform)
+            float zcull = zFar * kDepthTie;  // nothing beyond this depth can matter to any ray of the tile
+            // ---- tile frustum: the rays through the pixel centres, widened by half a pixel ----
+            const float XL = (tpx0 - 0.5f) * kx + cx, XR = (tpx0 + vw - 0.5f) * kx + cx;
+            const float YB = (tpy0 - 0.5f) * ky + cy, YT = (tpy0 + vh - 0.5f) * ky + cy;
+            float nx, ny, nz, thr;
+            switch (role) {
+                case 0: nx = sx - XL * fx; ny = sy - XL * fy; nz = sz - XL * fz; thr = -1e-4f; break;  // x >= XL z
+                case 1: nx = XR * fx - sx; ny = XR * fy - sy; nz = XR * fz - sz; thr = -1e-4f; break;  // x <= XR z
+                case 2: nx = ux - YB * fx; ny = uy - YB * fy; nz = uz - YB * fz; thr = -1e-4f; break;  // y >= YB z
+                case 3: nx = YT * fx - ux; ny = YT * fy - uy; nz = YT * fz - uz; thr = -1e-4f; break;  // y <= YT z
+                case 4: nx = fx; ny = fy; nz = fz; thr = zNear * 0.9999f - 1e-4f; break;                 // zmax >= zNear
+                default: nx = -fx; ny = -fy; nz = -fz; thr = 0.f; break;                                 // zmin <= zcull (limit set per node)
+            }
+            const float pixX0 = (float)(tpx0 + (lane & 7)), pixY0 = (float)(tpy0 + (lane >> 3));
+            __syncwarp();
+
+            // ---- frustum-packet traversal ----
+            int sp_ = 0;
+            int node = 0;
+            bool more = sc.T > 0;
+            while (more) {
+                const BvhNode* np = sc.nodes + node;
+                const float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
+                // this lane's child box, relative to the eye
+                const float bx0 = (second ? q1.z : q0.x) - ox, by0 = (second ? q1.w : q0.y) - oy, bz0 = (second ? q2.x : q0.z) - oz;
+                const float bx1 = (second ? q2.y : q0.w) - ox, by1 = (second ? q2.z : q1.x) - oy, bz1 = (second ? q2.w : q1.y) - oz;
+                // maximum of n.P over the box
+                const float m = (nx >= 0.f ? bx1 : bx0) * nx + (ny >= 0.f ? by1 : by0) * ny + (nz >= 0.f ? bz1 : bz0) * nz;
+                const float limit = role == 5 ? -(zcull * 1.000001f + 1e-4f) : thr;
+                const unsigned ok = __ballot_sync(0xffffffffu, m >= limit);
+                const bool h0 = (ok & 0x3fu) == 0x3fu, h1 = (ok & 0xfc0u) == 0xfc0u;
+                const float zmin0 = -__shfl_sync(0xffffffffu, m, 5), zmin1 = -__shfl_sync(0xffffffffu, m, 11);
+                const int l0 = __float_as_int(q3.x), l1 = __float_as_int(q3.y);
+                // ---- leaves ----
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int l = c ? l1 : l0;
+                    if (!(c ? h1 : h0) || l >= 0) continue;
+                    const int code = ~l;
+                    const int first = code >> kLeafShift, cnt = code & kLeafMask;
+                    __syncwarp();
+                    if (lane < cnt) {
+                        const float4 a = __ldg(sc.ta + first + lane), b = __ldg(sc.tb + first + lane), cc = __ldg(sc.tc + first + lane),
+                                     nn = __ldg(sc.tn + first + lane);
+                        float* o = S.tri[lane];
+                        float valid = 0.f;
+                        if (b.w == 0.f) {  // not degenerate
+                            float3 na, nb, nc, ap;
+                            edge_normals(a, b, cc, ox, oy, oz, na, nb, nc, ap);
+                            // camera-space depth of the vertices; the depth of a fragment is a convex combination of them
+                            const float bpx = b.x - ox, bpy = b.y - oy, bpz = b.z - oz, cpx = cc.x - ox, cpy = cc.y - oy, cpz = cc.z - oz;
+                            const float za = ap.x * fx + ap.y * fy + ap.z * fz, zb = bpx * fx + bpy * fy + bpz * fz,
+                                        zc = cpx * fx + cpy * fy + cpz * fz;
+                            const float zlo = fminf(za, fminf(zb, zc)), zhi = fmaxf(za, fmaxf(zb, zc));
+                            if (zhi >= zNear * 0.9999f && zlo <= zcull * 1.000001f) {
+                                int x0 = 0, x1 = vw - 1, y0 = 0, y1 = vh - 1;
+                                if (zlo > zNear * 0.5f) {
+                                    // all vertices in front of the eye: projected bounding rectangle in continuous pixel index
+                                    // (pixel centre i sits at index i), widened by 0.05 pixel against rounding
+                                    const float ia = 1.0f / za, ib = 1.0f / zb, ic = 1.0f / zc;
+                                    const float xa = (ap.x * sx + ap.y * sy + ap.z * sz) * ia, xb = (bpx * sx + bpy * sy + bpz * sz) * ib,
+                                                xc = (cpx * sx + cpy * sy + cpz * sz) * ic;
+                                    const float ya = (ap.x * ux + ap.y * uy + ap.z * uz) * ia, yb = (bpx * ux + bpy * uy + bpz * uz) * ib,
+                                                yc = (cpx * ux + cpy * uy + cpz * uz) * ic;
+                                    float fx0 = (fminf(xa, fminf(xb, xc)) - cx) * ikx - (float)tpx0, fx1 = (fmaxf(xa, fmaxf(xb, xc)) - cx) * ikx - (float)tpx0;
+                                    float fy0 = (fminf(ya, fminf(yb, yc)) - cy) * iky - (float)tpy0, fy1 = (fmaxf(ya, fmaxf(yb, yc)) - cy) * iky - (float)tpy0;
+                                    fx0 = fminf(fmaxf(fx0, -8.f), 72.f); fx1 = fminf(fmaxf(fx1, -8.f), 72.f);
+                                    fy0 = fminf(fmaxf(fy0, -8.f), 72.f); fy1 = fminf(fmaxf(fy1, -8.f), 72.f);
+                                    x0 = max(0, (int)floorf(fx0 - 0.05f));
+                                    x1 = min(vw - 1, (int)ceilf(fx1 + 0.05f));
+                                    y0 = max(0, (int)floorf(fy0 - 0.05f));
+                                    y1 = min(vh - 1, (int)ceilf(fy1 + 0.05f));
+                                }
+                                if (x0 <= x1 && y0 <= y1) {
+                                    valid = 1.f;
+                                    o[0] = na.x * fx + na.y * fy + na.z * fz; o[1] = na.x * sx + na.y * sy + na.z * sz; o[2] = na.x * ux + na.y * uy + na.z * uz;
+                                    o[3] = nb.x * fx + nb.y * fy + nb.z * fz; o[4] = nb.x * sx + nb.y * sy + nb.z * sz; o[5] = nb.x * ux + nb.y * uy + nb.z * uz;
+                                    o[6] = nc.x * fx + nc.y * fy + nc.z * fz; o[7] = nc.x * sx + nc.y * sy + nc.z * sz; o[8] = nc.x * ux + nc.y * uy + nc.z * uz;
+                                    o[9] = nn.x * fx + nn.y * fy + nn.z * fz; o[10] = nn.x * sx + nn.y * sy + nn.z * sz; o[11] = nn.x * ux + nn.y * uy + nn.z * uz;
+                                    o[12] = ap.x * nn.x + ap.y * nn.y + ap.z * nn.z;  // vol = A'.Ng
+                                    o[13] = a.w;                                       // triangle id (int bits)
+                                    o[14] = __int_as_float(x0 | (x1 << 8) | (y0 << 16) | (y1 << 24));
+                                }
+                            }
+                        }
+                        o[15] = valid;
+                    }
+                    __syncwarp();
+                    bool dirty = false;
+                    int firstHits = 0;
+                    for (int k = 0; k < cnt; ++k) {
+                        const float* tr = S.tri[k];
+                        if (tr[15] == 0.f) continue;
+                        const int box = __float_as_int(tr[14]);
+                        const int bxa = (box & 255) >> 3, bxb = ((box >> 8) & 255) >> 3, bya = ((box >> 16) & 255) >> 2, byb = ((box >> 24) & 255) >> 2;
+                        const float eaf = tr[0], eas = tr[1], eau = tr[2], ebf = tr[3], ebs = tr[4], ebu = tr[5], ecf = tr[6], ecs = tr[7],
+                                    ecu = tr[8], gf = tr[9], gs = tr[10], gu = tr[11], vol = tr[12];
+                        const int id = __float_as_int(tr[13]);
+                        for (int by = bya; by <= byb; ++by) {
+                            const float Y = (pixY0 + (float)(by * 4)) * ky + cy;
+                            const float ra = eau * Y + eaf, rb = ebu * Y + ebf, rc = ecu * Y + ecf, rg = gu * Y + gf;
+                            const bool rowOk = (by * 4 + (lane >> 3)) < vh;
+                            for (int bx = bxa; bx <= bxb; ++bx) {
+                                const float X = (pixX0 + (float)(bx * 8)) * kx + cx;
+                                const float eu = eas * X + ra, ev = ebs * X + rb, ew = ecs * X + rc;
+                                const bool in = (eu >= 0.f && ev >= 0.f && ew >= 0.f) || (eu <= 0.f && ev <= 0.f && ew <= 0.f);
+                                if (in && rowOk && (bx * 8 + (lane & 7)) < vw) {
+                                    const float det = gs * X + rg;
+                                    const float t = __fdividef(vol, det);  // det == 0: inf / NaN fails the range test
+                                    const int idx = (by * 4 + bx) * 32 + lane;
+                                    const float ht = S.t[idx];
+                                    if (t >= zNear && t <= zFar && t <= ht * kDepthTie) {
+                                        const int hid = S.id[idx];
+                                        S.id[idx] = (t * kDepthTie < ht) ? id : min(hid, id);
+                                        S.t[idx] = fminf(ht, t);
+                                        dirty = true;
+                                        firstHits += hid == kNoId ? 1 : 0;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, dirty)) {
+                        if (nEmpty > 0) {
+                            for (int o2 = 16; o2; o2 >>= 1) firstHits += __shfl_xor_sync(0xffffffffu, firstHits, o2);
+                            nEmpty -= firstHits;
+                        }
+                        if (nEmpty == 0) {
+                            // every ray has a hit: the farthest one bounds what can still matter (hierarchical depth culling)
+                            float zm = 0.f;
+#pragma unroll
+                            for (int k = 0; k < kTilePixels / 32; ++k) {
+                                const bool inside = ((k & 3) * 8 + (lane & 7)) < vw && ((k >> 2) * 4 + (lane >> 3)) < vh;
+                                zm = fmaxf(zm, inside ? S.t[k * 32 + lane] : 0.f);
+                            }
+                            for (int o2 = 16; o2; o2 >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o2));
+                            zcull = zm * kDepthTie;
+                        }
+                    }
+                }
+                // ---- inner children: nearer one first ----
+                const bool i0 = h0 && l0 >= 0, i1 = h1 && l1 >= 0;
+                if (i0 && i1) {
+                    const bool swap = zmin1 < zmin0;
+                    if (lane == 0) {
+                        S.stack[2 * sp_] = swap ? l0 : l1;
+                        S.stack[2 * sp_ + 1] = __float_as_int(swap ? zmin0 : zmin1);
+                    }
+                    sp_++;
+                    node = swap ? l1 : l0;
+                } else if (i0) {
+                    node = l0;
+                } else if (i1) {
+                    node = l1;
+                } else {
+                    more = false;
+                    __syncwarp();
+                    while (sp_ > 0) {
+                        --sp_;
+                        const int cand = S.stack[2 * sp_];
+                        const float zmin = __int_as_float(S.stack[2 * sp_ + 1]);
+                        if (zmin <= zcull * 1.000001f + 1e-4f) {  // still in front of the farthest hit
+                            node = cand;
+                            more = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- the winners: one byte store per run of equal ids inside an 8x4 block ----
+#pragma unroll 4
+            for (int k = 0; k < kTilePixels / 32; ++k) {
+                const int id = S.id[k * 32 + lane];
+                const int left = __shfl_up_sync(0xffffffffu, id, 1), up = __shfl_up_sync(0xffffffffu, id, 8);
+                const bool dupe = ((lane & 7) != 0 && left == id) || (lane >= 8 && up == id);
+                if (id != kNoId && !dupe) flags[(size_t)slot * sc.Tpad + id] = 1;
+                if (idImage) {
+                    const int px = tpx0 + (k & 3) * 8 + (lane & 7), py = tpy0 + (k >> 2) * 4 + (lane >> 3);
+                    if (px < cam.W && py < cam.H) idImage[(size_t)py * cam.W + px] = id == kNoId ? -1 : id;
+                }
+            }
+            if (lane == 0) myRays += (unsigned long long)(vw * vh);
+            __syncwarp();
         }
-        __syncthreads();
     }
-    // rays issued: one atomic per warp
-    for (int o = 16; o; o >>= 1) myRays += __shfl_down_sync(0xffffffffu, myRays, o);
     if (lane == 0 && myRays) atomicAdd(&counters[0], myRays);
 }
 
@@ -253,7 +388,7 @@ __global__ void k_zero_row_tail(int nSlots, int wordsPerSlot, const int* __restr
 // ---- BVH self test: every thread traces one ray through the BVH and by brute force ----
 __device__ void trace_single(const DeviceScene& sc, float ox, float oy, float oz, float dx, float dy, float dz, Hit& h) {
     h.t = 1e30f;
-    h.id = 0x7fffffff;
+    h.id = kNoId;
     float ix = safe_rcp(dx), iy = safe_rcp(dy), iz = safe_rcp(dz);
     int stack[kMaxDepth];
     int sp = 0, node = 0;
@@ -270,12 +405,9 @@ __device__ void trace_single(const DeviceScene& sc, float ox, float oy, float oz
             if (!hh[c]) continue;
             if (l[c] < 0) {
                 int code = ~l[c];
-                int first = code >> 3, cnt = code & 7;
-                for (int k = 0; k < cnt; ++k) {
-                    float4 s0, s1, s2, s3;
-                    tri_setup(sc.ta[first + k], sc.tb[first + k], sc.tc[first + k], sc.tn[first + k], ox, oy, oz, s0, s1, s2, s3);
-                    tri_test(s0, s1, s2, s3, dx, dy, dz, 0.f, 1e30f, h);
-                }
+                int first = code >> kLeafShift, cnt = code & kLeafMask;
+                for (int k = 0; k < cnt; ++k)
+                    ray_tri_test(sc.ta[first + k], sc.tb[first + k], sc.tc[first + k], sc.tn[first + k], ox, oy, oz, dx, dy, dz, 0.f, 1e30f, h);
             } else if (next < 0) {
                 next = l[c];
             } else if (sp < kMaxDepth) {
@@ -295,18 +427,14 @@ __global__ void k_bvh_selftest(DeviceScene sc, const float* __restrict__ rays, l
     float ox = rays[6 * i], oy = rays[6 * i + 1], oz = rays[6 * i + 2], dx = rays[6 * i + 3], dy = rays[6 * i + 4], dz = rays[6 * i + 5];
     Hit h;
     trace_single(sc, ox, oy, oz, dx, dy, dz, h);
-    idsBvh[i] = h.id == 0x7fffffff ? -1 : h.id;
+    idsBvh[i] = h.id == kNoId ? -1 : h.id;
     Hit b;
     b.t = 1e30f;
-    b.id = 0x7fffffff;
-    for (int k = 0; k < sc.T; ++k) {
-        float4 s0, s1, s2, s3;
-        tri_setup(sc.ta[k], sc.tb[k], sc.tc[k], sc.tn[k], ox, oy, oz, s0, s1, s2, s3);
-        tri_test(s0, s1, s2, s3, dx, dy, dz, 0.f, 1e30f, b);
-    }
+    b.id = kNoId;
+    for (int k = 0; k < sc.T; ++k) ray_tri_test(sc.ta[k], sc.tb[k], sc.tc[k], sc.tn[k], ox, oy, oz, dx, dy, dz, 0.f, 1e30f, b);
     // near-ties (two surfaces within rounding of each other along the ray) may be culled by the box test: same depth counts as agreement
-    bool same = (b.id == h.id) || (b.id != 0x7fffffff && h.id != 0x7fffffff && fabsf(b.t - h.t) <= 1e-5f * fmaxf(1.f, fabsf(b.t)));
-    idsBrute[i] = same ? idsBvh[i] : (b.id == 0x7fffffff ? -1 : b.id);
+    bool same = (b.id == h.id) || (b.id != kNoId && h.id != kNoId && fabsf(b.t - h.t) <= 1e-5f * fmaxf(1.f, fabsf(b.t)));
+    idsBrute[i] = same ? idsBvh[i] : (b.id == kNoId ? -1 : b.id);
     if (tOut) {
         tOut[2 * i] = h.t;
         tOut[2 * i + 1] = b.t;
@@ -319,6 +447,7 @@ int visibility_grid_blocks() {
     int dev = 0, sms = 148, perSM = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_visibility, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_visibility, kVisThreads, 0);
     if (perSM < 1) perSM = 1;
     return sms * perSM;
@@ -329,9 +458,9 @@ void launch_visibility(const DeviceScene& sc, const CameraParams& cam, const Sna
     if (totalTiles <= 0 || nSnaps <= 0) return;
     static int blocks = 0;
     if (!blocks) blocks = visibility_grid_blocks();
-    long long chunks = (totalTiles + kChunk - 1) / kChunk;
-    int grid = (int)std::min<long long>(blocks, chunks);
-    // counters[1] is the chunk cursor of this launch
+    long long groups = (totalTiles + (long long)kVisWarps * kGrab - 1) / ((long long)kVisWarps * kGrab);
+    int grid = (int)std::min<long long>(blocks, groups);
+    // counters[1] is the tile cursor of this launch
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
     k_visibility<<<grid, kVisThreads, 0, st>>>(sc, cam, d_snaps, d_tileOffset, nSnaps, (long long)totalTiles, d_flags, d_idImage, d_counters);
 }
