@@ -39,7 +39,22 @@ struct Hit {
     int id;
 };
 
+// a*b - c*d and a.b with a fixed rounding sequence.  Explicit intrinsics: the compiler may neither contract nor reassociate them, so
+// the same inputs give the same bits everywhere and negated inputs give exactly negated results -- the property the shared-edge
+// argument below rests on (-(x*y - z*w) silently rewritten as fma(z, w, -(x*y)) rounds the other product first and breaks it).
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) { return __fmaf_rn(a, b, -__fmul_rn(c, d)); }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+}
+
+__device__ __forceinline__ double ddiff(double a, double b, double c, double d) { return __fma_rn(a, b, -__dmul_rn(c, d)); }
+__device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
+    return __fma_rn(az, bz, __fma_rn(ay, by, __dmul_rn(ax, bx)));
+}
+
 // Edge normals with the eye at the origin.  e_a = D.Na, e_b = D.Nb, e_c = D.Nc are the homogeneous edge functions of a ray D.
+// Each normal is lowerEndpoint' x (upperEndpoint - lowerEndpoint) of its edge (vertices are stored lexicographically sorted), up to
+// sign: two triangles sharing an edge compute bit-identical normals up to sign.
 __device__ __forceinline__ void edge_normals(const float4 a, const float4 b, const float4 c, float ox, float oy, float oz, float3& na,
                                              float3& nb, float3& nc, float3& ap) {
     float ax = a.x - ox, ay = a.y - oy, az = a.z - oz;
@@ -48,9 +63,12 @@ __device__ __forceinline__ void edge_normals(const float4 a, const float4 b, con
     float ebcx = c.x - b.x, ebcy = c.y - b.y, ebcz = c.z - b.z;
     float eacx = c.x - a.x, eacy = c.y - a.y, eacz = c.z - a.z;
     float eabx = b.x - a.x, eaby = b.y - a.y, eabz = b.z - a.z;
-    na = make_float3(by * ebcz - bz * ebcy, bz * ebcx - bx * ebcz, bx * ebcy - by * ebcx);           // B' x (C-B)
-    nb = make_float3(-(ay * eacz - az * eacy), -(az * eacx - ax * eacz), -(ax * eacy - ay * eacx));  // C' x (A-C) = -(A' x (C-A))
-    nc = make_float3(ay * eabz - az * eaby, az * eabx - ax * eabz, ax * eaby - ay * eabx);           // A' x (B-A)
+    // B' x (C-B)
+    na = make_float3(diff_of_products(by, ebcz, bz, ebcy), diff_of_products(bz, ebcx, bx, ebcz), diff_of_products(bx, ebcy, by, ebcx));
+    // C' x (A-C) = -(A' x (C-A))
+    nb = make_float3(-diff_of_products(ay, eacz, az, eacy), -diff_of_products(az, eacx, ax, eacz), -diff_of_products(ax, eacy, ay, eacx));
+    // A' x (B-A)
+    nc = make_float3(diff_of_products(ay, eabz, az, eaby), diff_of_products(az, eabx, ax, eabz), diff_of_products(ax, eaby, ay, eabx));
     ap = make_float3(ax, ay, az);
 }
 
@@ -68,9 +86,9 @@ __device__ __forceinline__ void ray_tri_test(const float4 a, const float4 b, con
     if (b.w != 0.f) return;  // degenerate triangle: never produces a fragment
     float3 na, nb, nc, ap;
     edge_normals(a, b, c, ox, oy, oz, na, nb, nc, ap);
-    float eu = dx * na.x + dy * na.y + dz * na.z;
-    float ev = dx * nb.x + dy * nb.y + dz * nb.z;
-    float ew = dx * nc.x + dy * nc.y + dz * nc.z;
+    float eu = dot3(na.x, na.y, na.z, dx, dy, dz);
+    float ev = dot3(nb.x, nb.y, nb.z, dx, dy, dz);
+    float ew = dot3(nc.x, nc.y, nc.z, dx, dy, dz);
     bool in = (eu >= 0.f && ev >= 0.f && ew >= 0.f) || (eu <= 0.f && ev <= 0.f && ew <= 0.f);
     if (in) {
         float det = dx * n.x + dy * n.y + dz * n.z;
@@ -103,6 +121,51 @@ struct WarpShared {
     int stack[2 * kMaxDepth];        // (link, zmin bits) pairs
 };
 
+// One lane sets up one leaf triangle for the current camera pose: 16 floats in shared memory --
+//   [0..2] [3..5] [6..8] edge functions e(X, Y) = o[0] + o[1] X + o[2] Y of the pixel ray D = f + X s + Y u, [9..11] the same for
+//   det = D.Ng, [12] vol = (A - eye).Ng, [13] triangle id, [15] nearest vertex depth (< 0: produces no fragment in this tile).
+// Everything is multiplied by sign(vol), so that a ray in front of the eye crosses the triangle iff all three edge functions are
+// >= 0 and det > 0.  Setup runs in fp64 from the exact fp32 vertices, the fp32 eye and the fp64 camera basis; only the final
+// coefficients are rounded to fp32 (in fp32 the normal of an edge that points at the camera, |A' x e| << |A'||e|, lost up to
+// 0.03 pixel).
+__device__ __forceinline__ void setup_triangle(const DeviceScene& sc, const Snapshot* __restrict__ sp, int tri, float* __restrict__ o, float ox,
+                                               float oy, float oz, float zNear, float zcull) {
+    const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
+    float valid = -1.f;
+    if (b.w == 0.f) {  // not degenerate
+        const double fX = __ldg(&sp->f[0]), fY = __ldg(&sp->f[1]), fZ = __ldg(&sp->f[2]);
+        const double ax = (double)a.x - (double)ox, ay = (double)a.y - (double)oy, az = (double)a.z - (double)oz;
+        const double bx_ = (double)b.x - (double)ox, by_ = (double)b.y - (double)oy, bz_ = (double)b.z - (double)oz;
+        const double cx_ = (double)cc.x - (double)ox, cy_ = (double)cc.y - (double)oy, cz_ = (double)cc.z - (double)oz;
+        // camera-space depth of the vertices; the depth of a fragment is a convex combination of them
+        const float za = (float)ddot(ax, ay, az, fX, fY, fZ), zb = (float)ddot(bx_, by_, bz_, fX, fY, fZ),
+                    zc = (float)ddot(cx_, cy_, cz_, fX, fY, fZ);
+        const float zlo = fminf(za, fminf(zb, zc)), zhi = fmaxf(za, fmaxf(zb, zc));
+        if (zhi >= zNear * 0.9999f && zlo <= zcull * 1.000001f) {
+            const double sX = __ldg(&sp->s[0]), sY = __ldg(&sp->s[1]), sZ = __ldg(&sp->s[2]);
+            const double uX = __ldg(&sp->u[0]), uY = __ldg(&sp->u[1]), uZ = __ldg(&sp->u[2]);
+            const double ebcx = (double)cc.x - (double)b.x, ebcy = (double)cc.y - (double)b.y, ebcz = (double)cc.z - (double)b.z;
+            const double eacx = (double)cc.x - (double)a.x, eacy = (double)cc.y - (double)a.y, eacz = (double)cc.z - (double)a.z;
+            const double eabx = (double)b.x - (double)a.x, eaby = (double)b.y - (double)a.y, eabz = (double)b.z - (double)a.z;
+            // B' x (C-B);  C' x (A-C) = -(A' x (C-A));  A' x (B-A);  Ng = (B-A) x (C-A): every edge normal from the lower endpoint
+            const double nax = ddiff(by_, ebcz, bz_, ebcy), nay = ddiff(bz_, ebcx, bx_, ebcz), naz = ddiff(bx_, ebcy, by_, ebcx);
+            const double nbx = -ddiff(ay, eacz, az, eacy), nby = -ddiff(az, eacx, ax, eacz), nbz = -ddiff(ax, eacy, ay, eacx);
+            const double ncx = ddiff(ay, eabz, az, eaby), ncy = ddiff(az, eabx, ax, eabz), ncz = ddiff(ax, eaby, ay, eabx);
+            const double ngx = ddiff(eaby, eacz, eabz, eacy), ngy = ddiff(eabz, eacx, eabx, eacz), ngz = ddiff(eabx, eacy, eaby, eacx);
+            const double vol = ddot(ax, ay, az, ngx, ngy, ngz);  // (A - eye).Ng
+            const float sg = vol < 0.0 ? -1.f : 1.f;             // exact sign flip: shared edges stay bit-identical up to sign
+            valid = fmaxf(zlo, 0.f) * 0.999999f;
+            o[0] = sg * (float)ddot(nax, nay, naz, fX, fY, fZ); o[1] = sg * (float)ddot(nax, nay, naz, sX, sY, sZ); o[2] = sg * (float)ddot(nax, nay, naz, uX, uY, uZ);
+            o[3] = sg * (float)ddot(nbx, nby, nbz, fX, fY, fZ); o[4] = sg * (float)ddot(nbx, nby, nbz, sX, sY, sZ); o[5] = sg * (float)ddot(nbx, nby, nbz, uX, uY, uZ);
+            o[6] = sg * (float)ddot(ncx, ncy, ncz, fX, fY, fZ); o[7] = sg * (float)ddot(ncx, ncy, ncz, sX, sY, sZ); o[8] = sg * (float)ddot(ncx, ncy, ncz, uX, uY, uZ);
+            o[9] = sg * (float)ddot(ngx, ngy, ngz, fX, fY, fZ); o[10] = sg * (float)ddot(ngx, ngy, ngz, sX, sY, sZ); o[11] = sg * (float)ddot(ngx, ngy, ngz, uX, uY, uZ);
+            o[12] = sg * (float)vol;
+            o[13] = a.w;  // triangle id (int bits)
+        }
+    }
+    o[15] = valid;
+}
+
 // last index s in [0, nSnaps) with tileOffset[s] <= task (tileOffset[0] == 0): 32-ary search, one probe per lane and round
 __device__ __forceinline__ int find_snapshot(const int* __restrict__ tileOffset, int nSnaps, long long task, int lane) {
     int lo = 0, hi = nSnaps - 1;
@@ -131,7 +194,6 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
     // pixel-centre image-plane coordinates: X(px) = ((px + 0.5) / W * 2 - 1) tanX = px kx + cx
     const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
     const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
-    const float ikx = 1.0f / kx, iky = 1.0f / ky;
     const float zNear = cam.zNear, zFar = cam.zFar;
     // this lane's role in the node test: child = lane / 6, quantity = lane % 6 (lanes >= 12 idle)
     const int role = lane < 12 ? lane % 6 : 0;
@@ -161,14 +223,17 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
             const int local = (int)(task - __ldg(tileOffset + si));
             const int tpx0 = (rx0 + local % rnx) * kTile, tpy0 = (ry0 + local / rnx) * kTile;
             // ---- tile state ----
+            const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
 #pragma unroll
             for (int k = 0; k < kTilePixels / 32; ++k) {
-                S.t[k * 32 + lane] = zFar;
+                // rays outside the image start with depth 0: no fragment can ever beat it
+                const bool inside = ((k & 3) * 8 + (lane & 7)) < vw && ((k >> 2) * 4 + (lane >> 3)) < vh;
+                S.t[k * 32 + lane] = inside ? zFar : 0.f;
                 S.id[k * 32 + lane] = kNoId;
             }
-            const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
-            int nEmpty = vw * vh;            // rays without a hit yet (warp-uniform)
             float zcull = zFar * kDepthTie;  // nothing beyond this depth can matter to any ray of the tile
+            // lane b keeps the depth beyond which nothing can matter to any ray of 8x4 block b (0: block outside the image)
+            float bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zcull : 0.f;
             // ---- tile frustum: the rays through the pixel centres, widened by half a pixel ----
             const float XL = (tpx0 - 0.5f) * kx + cx, XR = (tpx0 + vw - 0.5f) * kx + cx;
             const float YB = (tpy0 - 0.5f) * ky + cy, YT = (tpy0 + vh - 0.5f) * ky + cy;
@@ -181,7 +246,13 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
                 case 4: nx = fx; ny = fy; nz = fz; thr = zNear * 0.9999f - 1e-4f; break;                 // zmax >= zNear
                 default: nx = -fx; ny = -fy; nz = -fz; thr = 0.f; break;                                 // zmin <= zcull (limit set per node)
             }
-            const float pixX0 = (float)(tpx0 + (lane & 7)), pixY0 = (float)(tpy0 + (lane >> 3));
+            // image-plane position of this lane's pixel in block (0, 0); block (bx, by) adds (bx 8 kx, by 4 ky).  The same
+            // expression is used for a pixel whatever triangle is tested, so shared edges stay watertight.
+            const float Xl = __fmaf_rn((float)(tpx0 + (lane & 7)), kx, cx), Yl = __fmaf_rn((float)(tpy0 + (lane >> 3)), ky, cy);
+            const float kx8 = 8.f * kx, ky4 = 4.f * ky;
+            // extreme pixel centres of block b = lane, by the same expressions its corner pixels use
+            const float bXmin = __fmaf_rn((float)(lane & 3), kx8, __fmaf_rn((float)tpx0, kx, cx)), bXmax = __fmaf_rn((float)(lane & 3), kx8, __fmaf_rn((float)(tpx0 + 7), kx, cx));
+            const float bYmin = __fmaf_rn((float)(lane >> 2), ky4, __fmaf_rn((float)tpy0, ky, cy)), bYmax = __fmaf_rn((float)(lane >> 2), ky4, __fmaf_rn((float)(tpy0 + 3), ky, cy));
             __syncwarp();
 
             // ---- frustum-packet traversal ----
@@ -209,103 +280,53 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
                     const int code = ~l;
                     const int first = code >> kLeafShift, cnt = code & kLeafMask;
                     __syncwarp();
-                    if (lane < cnt) {
-                        const float4 a = __ldg(sc.ta + first + lane), b = __ldg(sc.tb + first + lane), cc = __ldg(sc.tc + first + lane),
-                                     nn = __ldg(sc.tn + first + lane);
-                        float* o = S.tri[lane];
-                        float valid = 0.f;
-                        if (b.w == 0.f) {  // not degenerate
-                            float3 na, nb, nc, ap;
-                            edge_normals(a, b, cc, ox, oy, oz, na, nb, nc, ap);
-                            // camera-space depth of the vertices; the depth of a fragment is a convex combination of them
-                            const float bpx = b.x - ox, bpy = b.y - oy, bpz = b.z - oz, cpx = cc.x - ox, cpy = cc.y - oy, cpz = cc.z - oz;
-                            const float za = ap.x * fx + ap.y * fy + ap.z * fz, zb = bpx * fx + bpy * fy + bpz * fz,
-                                        zc = cpx * fx + cpy * fy + cpz * fz;
-                            const float zlo = fminf(za, fminf(zb, zc)), zhi = fmaxf(za, fmaxf(zb, zc));
-                            if (zhi >= zNear * 0.9999f && zlo <= zcull * 1.000001f) {
-                                int x0 = 0, x1 = vw - 1, y0 = 0, y1 = vh - 1;
-                                if (zlo > zNear * 0.5f) {
-                                    // all vertices in front of the eye: projected bounding rectangle in continuous pixel index
-                                    // (pixel centre i sits at index i), widened by 0.05 pixel against rounding
-                                    const float ia = 1.0f / za, ib = 1.0f / zb, ic = 1.0f / zc;
-                                    const float xa = (ap.x * sx + ap.y * sy + ap.z * sz) * ia, xb = (bpx * sx + bpy * sy + bpz * sz) * ib,
-                                                xc = (cpx * sx + cpy * sy + cpz * sz) * ic;
-                                    const float ya = (ap.x * ux + ap.y * uy + ap.z * uz) * ia, yb = (bpx * ux + bpy * uy + bpz * uz) * ib,
-                                                yc = (cpx * ux + cpy * uy + cpz * uz) * ic;
-                                    float fx0 = (fminf(xa, fminf(xb, xc)) - cx) * ikx - (float)tpx0, fx1 = (fmaxf(xa, fmaxf(xb, xc)) - cx) * ikx - (float)tpx0;
-                                    float fy0 = (fminf(ya, fminf(yb, yc)) - cy) * iky - (float)tpy0, fy1 = (fmaxf(ya, fmaxf(yb, yc)) - cy) * iky - (float)tpy0;
-                                    fx0 = fminf(fmaxf(fx0, -8.f), 72.f); fx1 = fminf(fmaxf(fx1, -8.f), 72.f);
-                                    fy0 = fminf(fmaxf(fy0, -8.f), 72.f); fy1 = fminf(fmaxf(fy1, -8.f), 72.f);
-                                    x0 = max(0, (int)floorf(fx0 - 0.05f));
-                                    x1 = min(vw - 1, (int)ceilf(fx1 + 0.05f));
-                                    y0 = max(0, (int)floorf(fy0 - 0.05f));
-                                    y1 = min(vh - 1, (int)ceilf(fy1 + 0.05f));
-                                }
-                                if (x0 <= x1 && y0 <= y1) {
-                                    valid = 1.f;
-                                    o[0] = na.x * fx + na.y * fy + na.z * fz; o[1] = na.x * sx + na.y * sy + na.z * sz; o[2] = na.x * ux + na.y * uy + na.z * uz;
-                                    o[3] = nb.x * fx + nb.y * fy + nb.z * fz; o[4] = nb.x * sx + nb.y * sy + nb.z * sz; o[5] = nb.x * ux + nb.y * uy + nb.z * uz;
-                                    o[6] = nc.x * fx + nc.y * fy + nc.z * fz; o[7] = nc.x * sx + nc.y * sy + nc.z * sz; o[8] = nc.x * ux + nc.y * uy + nc.z * uz;
-                                    o[9] = nn.x * fx + nn.y * fy + nn.z * fz; o[10] = nn.x * sx + nn.y * sy + nn.z * sz; o[11] = nn.x * ux + nn.y * uy + nn.z * uz;
-                                    o[12] = ap.x * nn.x + ap.y * nn.y + ap.z * nn.z;  // vol = A'.Ng
-                                    o[13] = a.w;                                       // triangle id (int bits)
-                                    o[14] = __int_as_float(x0 | (x1 << 8) | (y0 << 16) | (y1 << 24));
-                                }
-                            }
-                        }
-                        o[15] = valid;
-                    }
+                    if (lane < cnt) setup_triangle(sc, snaps + si, first + lane, S.tri[lane], ox, oy, oz, zNear, zcull);
                     __syncwarp();
                     bool dirty = false;
-                    int firstHits = 0;
                     for (int k = 0; k < cnt; ++k) {
                         const float* tr = S.tri[k];
-                        if (tr[15] == 0.f) continue;
-                        const int box = __float_as_int(tr[14]);
-                        const int bxa = (box & 255) >> 3, bxb = ((box >> 8) & 255) >> 3, bya = ((box >> 16) & 255) >> 2, byb = ((box >> 24) & 255) >> 2;
+                        const float zloTri = tr[15];
+                        if (zloTri < 0.f || zloTri > zcull) continue;
                         const float eaf = tr[0], eas = tr[1], eau = tr[2], ebf = tr[3], ebs = tr[4], ebu = tr[5], ecf = tr[6], ecs = tr[7],
                                     ecu = tr[8], gf = tr[9], gs = tr[10], gu = tr[11], vol = tr[12];
                         const int id = __float_as_int(tr[13]);
-                        for (int by = bya; by <= byb; ++by) {
-                            const float Y = (pixY0 + (float)(by * 4)) * ky + cy;
-                            const float ra = eau * Y + eaf, rb = ebu * Y + ebf, rc = ecu * Y + ecf, rg = gu * Y + gf;
-                            const bool rowOk = (by * 4 + (lane >> 3)) < vh;
-                            for (int bx = bxa; bx <= bxb; ++bx) {
-                                const float X = (pixX0 + (float)(bx * 8)) * kx + cx;
-                                const float eu = eas * X + ra, ev = ebs * X + rb, ew = ecs * X + rc;
-                                const bool in = (eu >= 0.f && ev >= 0.f && ew >= 0.f) || (eu <= 0.f && ev <= 0.f && ew <= 0.f);
-                                if (in && rowOk && (bx * 8 + (lane & 7)) < vw) {
-                                    const float det = gs * X + rg;
-                                    const float t = __fdividef(vol, det);  // det == 0: inf / NaN fails the range test
-                                    const int idx = (by * 4 + bx) * 32 + lane;
-                                    const float ht = S.t[idx];
-                                    if (t >= zNear && t <= zFar && t <= ht * kDepthTie) {
-                                        const int hid = S.id[idx];
-                                        S.id[idx] = (t * kDepthTie < ht) ? id : min(hid, id);
-                                        S.t[idx] = fminf(ht, t);
-                                        dirty = true;
-                                        firstHits += hid == kNoId ? 1 : 0;
-                                    }
+                        // which 8x4 blocks can hold a fragment that matters: lane b answers for block b.  An edge function is
+                        // monotone in X and in Y, also as computed, so its value at the extreme pixel centre bounds the block.
+                        const float ca = __fmaf_rn(eas, eas >= 0.f ? bXmax : bXmin, __fmaf_rn(eau, eau >= 0.f ? bYmax : bYmin, eaf));
+                        const float cb = __fmaf_rn(ebs, ebs >= 0.f ? bXmax : bXmin, __fmaf_rn(ebu, ebu >= 0.f ? bYmax : bYmin, ebf));
+                        const float cc = __fmaf_rn(ecs, ecs >= 0.f ? bXmax : bXmin, __fmaf_rn(ecu, ecu >= 0.f ? bYmax : bYmin, ecf));
+                        unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && zloTri <= bzReg);
+                        while (todo) {
+                            const int blk = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const float X = __fmaf_rn((float)(blk & 3), kx8, Xl), Y = __fmaf_rn((float)(blk >> 2), ky4, Yl);
+                            const float eu = __fmaf_rn(eas, X, __fmaf_rn(eau, Y, eaf)), ev = __fmaf_rn(ebs, X, __fmaf_rn(ebu, Y, ebf)),
+                                        ew = __fmaf_rn(ecs, X, __fmaf_rn(ecu, Y, ecf));
+                            if (fminf(fminf(eu, ev), ew) >= 0.f) {  // the ray crosses the triangle
+                                const float det = gs * X + (gu * Y + gf);
+                                const float t = __fdividef(vol, det);  // det == 0: inf / NaN fails the range test
+                                const int idx = blk * 32 + lane;
+                                const float ht = S.t[idx];
+                                if (t >= zNear && t <= zFar && t <= ht * kDepthTie) {
+                                    const int hid = S.id[idx];
+                                    S.id[idx] = (t * kDepthTie < ht) ? id : min(hid, id);
+                                    S.t[idx] = fminf(ht, t);
+                                    dirty = true;
                                 }
                             }
                         }
                     }
                     if (__any_sync(0xffffffffu, dirty)) {
-                        if (nEmpty > 0) {
-                            for (int o2 = 16; o2; o2 >>= 1) firstHits += __shfl_xor_sync(0xffffffffu, firstHits, o2);
-                            nEmpty -= firstHits;
-                        }
-                        if (nEmpty == 0) {
-                            // every ray has a hit: the farthest one bounds what can still matter (hierarchical depth culling)
-                            float zm = 0.f;
-#pragma unroll
-                            for (int k = 0; k < kTilePixels / 32; ++k) {
-                                const bool inside = ((k & 3) * 8 + (lane & 7)) < vw && ((k >> 2) * 4 + (lane >> 3)) < vh;
-                                zm = fmaxf(zm, inside ? S.t[k * 32 + lane] : 0.f);
-                            }
-                            for (int o2 = 16; o2; o2 >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o2));
-                            zcull = zm * kDepthTie;
-                        }
+                        // hierarchical depth culling: lane b takes the farthest hit of block b (conflict-free diagonal walk);
+                        // rays without a hit still hold zFar, rays outside the image hold 0
+                        __syncwarp();
+                        float zm = 0.f;
+#pragma unroll 8
+                        for (int j = 0; j < 32; ++j) zm = fmaxf(zm, S.t[lane * 32 + ((j + lane) & 31)]);
+                        zm *= kDepthTie;
+                        bzReg = zm;
+                        for (int o2 = 16; o2; o2 >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o2));
+                        zcull = zm;
                     }
                 }
                 // ---- inner children: nearer one first ----
