@@ -283,6 +283,7 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_total = allmax(ms.value)
     cnt = ev.counters()
+    vstat = ev.visibility_stats()
     vis_ms, vis_n = ev.kernel_time(1)
     red_ms, red_n = ev.kernel_time(0)
     col_ms, col_n = ev.kernel_time(2)
@@ -361,11 +362,14 @@ def run_gpu(args):
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # one pixel-centre occlusion query = one root-to-leaf descent fetching both 32-byte child boxes per level + one 48-byte triangle
-    b_ray = 2 * math.ceil(math.log2(T)) * 32 + 48
+    # K4 reads 64 B per BVH node a tile packet fetches and 48 B per triangle it stages; both counts are data
+    # dependent and come from the kernel's own device counters for exactly the timed launches.
+    alg_bytes_launch = (64.0 * vstat["nodes"] + 48.0 * vstat["triangles"]) / max(1, vis_n)
     rays_launch = cnt["rays"] / max(1, vis_n)
     vis_launch_s = vis_ms / max(1, vis_n) * 1e-3
-    achieved = rays_launch * b_ray / vis_launch_s / 1e9 if vis_launch_s > 0 else 0.0
+    achieved = alg_bytes_launch / vis_launch_s / 1e9 if vis_launch_s > 0 else 0.0
+    # SURVEY 8(d)'s independent-ray model, for reference: one root-to-leaf descent (2 x 32 B boxes per level) + one 48 B triangle per ray
+    b_ray = 2 * math.ceil(math.log2(T)) * 32 + 48
     pop_total = world * POP
     value = pop_total * args.steps / (ms_total * 1e-3)
     e2e_value = pop_total * args.steps / (ms_e2e * 1e-3)
@@ -384,11 +388,14 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(pop_total * 4 * 8), "ms_per_step": ms_e2e / args.steps, "matches_resident_path": bool(same)},
         "gpu_launches": int(cnt["launches"]),
         "roofline": {"kernel": "k_visibility", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None, "bytes_per_ray": b_ray, "rays_per_launch": rays_launch, "us_per_launch": vis_launch_s * 1e6,
+                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes_launch, "us_per_launch": vis_launch_s * 1e6,
+                     "tiles_per_launch": vstat["tiles"] / max(1, vis_n), "nodes_per_tile": vstat["nodes"] / max(1, vstat["tiles"]),
+                     "triangles_per_tile": vstat["triangles"] / max(1, vstat["tiles"]), "rays_per_launch": rays_launch,
                      "peak_source": peak_src,
-                     "note": "algorithmic bytes per SURVEY 8(d) are requests to the memory hierarchy; the 3.4 MB BVH + 1.7 MB triangles stay "
-                             "in L1/L2, so DRAM traffic (ncu, profiles/) is far below them and frac can exceed 1: the kernel is "
-                             "latency/issue-bound, not HBM-bound"},
+                     "survey_independent_ray_model": {"bytes_per_ray": b_ray, "gbs": rays_launch * b_ray / vis_launch_s / 1e9 if vis_launch_s > 0 else 0.0,
+                                                      "note": "what 1024 independent rays per tile would have requested; the tile packet shares the descent"},
+                     "note": "bytes = 64 B per BVH node fetched + 48 B per triangle staged, counted on the device; the 1.7 MB BVH + 1.3 MB "
+                             "triangles stay in L1/L2 (ncu: DRAM traffic in profiles/), the kernel is issue/latency bound, not HBM bound"},
         "roofline_plan_reduce": warm,
     }
     # CPU baseline beside it: the CPU restatement on this box's host cores, bounded sample

@@ -146,6 +146,9 @@ int ipp_flush_l2(ipp_t* h);
 /* counters since the last reset: [0] kernel launches, [1] pixel-centre rays issued, [2] snapshots rendered,
  * [3] edges rendered, [4] collision queries, [5] plan_reduce launches, [6] plans reduced, [7] bitmap rows read */
 int ipp_counters(ipp_t* h, int64_t* out8, int reset);
+/* traversal statistics of the edge-visibility kernel since the last reset (reset by ipp_counters too):
+ * [0] BVH nodes fetched (64 B each), [1] triangles staged (48 B each), [2] 32x32-pixel tiles, [3] pixel-centre rays */
+int ipp_visibility_stats(ipp_t* h, int64_t* out4, int reset);
 /* accumulated CUDA-event time of a named kernel group since the last reset:
  * 0 = plan_reduce, 1 = edge_visibility, 2 = edge_collision, 3 = pack, 4 = energy+mark */
 int ipp_kernel_time(ipp_t* h, int which, double* ms, int64_t* launches, int reset);

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "ipp_timer_stop": (C.c_int, [H, c_f64p]),
     "ipp_flush_l2": (C.c_int, [H]),
     "ipp_counters": (C.c_int, [H, c_i64p, C.c_int]),
+    "ipp_visibility_stats": (C.c_int, [H, c_i64p, C.c_int]),
     "ipp_kernel_time": (C.c_int, [H, C.c_int, c_f64p, c_i64p, C.c_int]),
     "ipp_set_profiling": (C.c_int, [H, C.c_int]),
     "ipp_comm_unique_id": (C.c_int, [c_u8p]),

@@ -276,6 +276,11 @@ class PlanCoverageEstimator(object):
         keys = ["launches", "rays", "snapshots", "edges_rendered", "collision_queries", "reduce_launches", "plans_reduced", "rows_read"]
         return dict(zip(keys, (int(x) for x in out)))
 
+    def visibility_stats(self, reset=False):
+        out = np.zeros(4, dtype=np.int64)
+        _lib.check(self._L.ipp_visibility_stats(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
+        return dict(zip(["nodes", "triangles", "tiles", "rays"], (int(x) for x in out)))
+
     def kernel_time(self, which, reset=False):
         ms, n = C.c_double(), C.c_int64()
         _lib.check(self._L.ipp_kernel_time(self._h, int(which), C.byref(ms), C.byref(n), int(reset)))

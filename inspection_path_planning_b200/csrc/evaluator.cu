@@ -96,8 +96,8 @@ Evaluator::Evaluator(const std::string& scenePath, const double specs[8], bool p
     // ---- scalars ----
     d_scalars_ = dalloc<int>(8);
     IPP_CUDA_CHECK(cudaHostAlloc((void**)&h_scalars_, 8 * sizeof(int), cudaHostAllocDefault));
-    d_visCounters_ = dalloc<unsigned long long>(2);
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 2 * sizeof(unsigned long long), stream_));
+    d_visCounters_ = dalloc<unsigned long long>(8);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
     d_angleOne_ = dalloc<float>(1);
 
     // ---- candidate viewpoints (PlanInterpreterBoxOrder::divideIntoBoxes :193-251) ----
@@ -272,8 +272,16 @@ void Evaluator::counters(int64_t out[8], bool reset) {
     out[4] = nCollisionQueries_; out[5] = nReduceLaunches_; out[6] = nPlansReduced_; out[7] = nRowsRead_;
     if (reset) {
         nLaunches_ = nSnapshots_ = nEdgesRendered_ = nCollisionQueries_ = nReduceLaunches_ = nPlansReduced_ = nRowsRead_ = 0;
-        IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, sizeof(unsigned long long), stream_));
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
     }
+}
+void Evaluator::visibilityStats(int64_t out[4], bool reset) {
+    bind();
+    unsigned long long c[8];
+    IPP_CUDA_CHECK(cudaMemcpyAsync(c, d_visCounters_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    out[0] = (int64_t)c[2]; out[1] = (int64_t)c[3]; out[2] = (int64_t)c[4]; out[3] = (int64_t)c[0];
+    if (reset) IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
 }
 void Evaluator::timerStart() {
     bind();

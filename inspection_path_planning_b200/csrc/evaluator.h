@@ -50,6 +50,7 @@ class Evaluator {
     double timerStop();
     void flushL2();
     void counters(int64_t out[8], bool reset);
+    void visibilityStats(int64_t out[4], bool reset);
     void kernelTime(int which, double* ms, int64_t* launches, bool reset);
     void setProfiling(bool on) { profiling_ = on; }
     cudaStream_t stream() const { return stream_; }
@@ -110,7 +111,7 @@ class Evaluator {
     int64_t snapCap_ = 0;
     void* d_scanTmp_ = nullptr;
     size_t scanTmpBytes_ = 0;
-    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] chunk cursor
+    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] tile cursor, [2] nodes fetched, [3] triangles staged, [4] tiles
     float* d_angleOne_ = nullptr;
 
     // plan buffers (host-pointer entry point)

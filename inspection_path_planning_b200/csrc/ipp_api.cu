@@ -264,6 +264,11 @@ int ipp_counters(ipp_t* h, int64_t* out8, int reset) {
     E(h).counters(out8, reset != 0);
     IPP_CATCH
 }
+int ipp_visibility_stats(ipp_t* h, int64_t* out4, int reset) {
+    IPP_TRY
+    E(h).visibilityStats(out4, reset != 0);
+    IPP_CATCH
+}
 int ipp_kernel_time(ipp_t* h, int which, double* ms, int64_t* launches, int reset) {
     IPP_TRY
     E(h).kernelTime(which, ms, launches, reset != 0);

@@ -119,6 +119,7 @@ struct WarpShared {
     int id[kTilePixels];             // its triangle
     float tri[kLeafMax][kTriWords];  // staged leaf triangles
     int stack[2 * kMaxDepth];        // (link, zmin bits) pairs
+    Snapshot snap;                   // the camera pose of the current tile
 };
 
 // One lane sets up one leaf triangle for the current camera pose: 16 floats in shared memory --
@@ -128,12 +129,12 @@ struct WarpShared {
 // >= 0 and det > 0.  Setup runs in fp64 from the exact fp32 vertices, the fp32 eye and the fp64 camera basis; only the final
 // coefficients are rounded to fp32 (in fp32 the normal of an edge that points at the camera, |A' x e| << |A'||e|, lost up to
 // 0.03 pixel).
-__device__ __forceinline__ void setup_triangle(const DeviceScene& sc, const Snapshot* __restrict__ sp, int tri, float* __restrict__ o, float ox,
+__device__ __forceinline__ void setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
                                                float oy, float oz, float zNear, float zcull) {
     const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
     float valid = -1.f;
     if (b.w == 0.f) {  // not degenerate
-        const double fX = __ldg(&sp->f[0]), fY = __ldg(&sp->f[1]), fZ = __ldg(&sp->f[2]);
+        const double fX = sp->f[0], fY = sp->f[1], fZ = sp->f[2];
         const double ax = (double)a.x - (double)ox, ay = (double)a.y - (double)oy, az = (double)a.z - (double)oz;
         const double bx_ = (double)b.x - (double)ox, by_ = (double)b.y - (double)oy, bz_ = (double)b.z - (double)oz;
         const double cx_ = (double)cc.x - (double)ox, cy_ = (double)cc.y - (double)oy, cz_ = (double)cc.z - (double)oz;
@@ -142,8 +143,8 @@ __device__ __forceinline__ void setup_triangle(const DeviceScene& sc, const Snap
                     zc = (float)ddot(cx_, cy_, cz_, fX, fY, fZ);
         const float zlo = fminf(za, fminf(zb, zc)), zhi = fmaxf(za, fmaxf(zb, zc));
         if (zhi >= zNear * 0.9999f && zlo <= zcull * 1.000001f) {
-            const double sX = __ldg(&sp->s[0]), sY = __ldg(&sp->s[1]), sZ = __ldg(&sp->s[2]);
-            const double uX = __ldg(&sp->u[0]), uY = __ldg(&sp->u[1]), uZ = __ldg(&sp->u[2]);
+            const double sX = sp->s[0], sY = sp->s[1], sZ = sp->s[2];
+            const double uX = sp->u[0], uY = sp->u[1], uZ = sp->u[2];
             const double ebcx = (double)cc.x - (double)b.x, ebcy = (double)cc.y - (double)b.y, ebcz = (double)cc.z - (double)b.z;
             const double eacx = (double)cc.x - (double)a.x, eacy = (double)cc.y - (double)a.y, eacz = (double)cc.z - (double)a.z;
             const double eabx = (double)b.x - (double)a.x, eaby = (double)b.y - (double)a.y, eabz = (double)b.z - (double)a.z;
@@ -183,7 +184,7 @@ __device__ __forceinline__ int find_snapshot(const int* __restrict__ tileOffset,
     return lo;
 }
 
-__global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
+__global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
                                                             const int* __restrict__ tileOffset, int nSnaps, long long totalTiles,
                                                             uint8_t* __restrict__ flags, int32_t* __restrict__ idImage,
                                                             unsigned long long* __restrict__ counters) {
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpShared& S = s_all[warp];
     unsigned long long myRays = 0;
+    unsigned myNodes = 0, myTris = 0, myTiles = 0;  // traversal statistics (lane 0 only): nodes fetched, triangles staged, tiles
     // pixel-centre image-plane coordinates: X(px) = ((px + 0.5) / W * 2 - 1) tanX = px kx + cx
     const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
     const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
@@ -207,19 +209,22 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
         const long long end = base + kGrab < totalTiles ? base + kGrab : totalTiles;
         int si = find_snapshot(tileOffset, nSnaps, base, lane);
         int loaded = -1;
-        float ox = 0, oy = 0, oz = 0, fx = 0, fy = 0, fz = 0, sx = 0, sy = 0, sz = 0, ux = 0, uy = 0, uz = 0;
-        int slot = 0, rx0 = 0, ry0 = 0, rnx = 1;
+        float ox = 0, oy = 0, oz = 0;
         for (long long task = base; task < end; ++task) {
             while ((long long)__ldg(tileOffset + si + 1) <= task) si++;  // skips culled (empty) snapshots
             if (si != loaded) {
-                const Snapshot* sp = snaps + si;
-                fx = (float)sp->f[0]; fy = (float)sp->f[1]; fz = (float)sp->f[2];
-                sx = (float)sp->s[0]; sy = (float)sp->s[1]; sz = (float)sp->s[2];
-                ux = (float)sp->u[0]; uy = (float)sp->u[1]; uz = (float)sp->u[2];
-                ox = sp->eye[0]; oy = sp->eye[1]; oz = sp->eye[2];
-                slot = sp->slot; rx0 = sp->rx0; ry0 = sp->ry0; rnx = sp->rnx;
+                __syncwarp();
+                const int* src = (const int*)(snaps + si);
+                int* dst = (int*)&S.snap;
+                if (lane < (int)(sizeof(Snapshot) / 4)) dst[lane] = __ldg(src + lane);
+                __syncwarp();
+                ox = S.snap.eye[0]; oy = S.snap.eye[1]; oz = S.snap.eye[2];
                 loaded = si;
             }
+            const float fx = (float)S.snap.f[0], fy = (float)S.snap.f[1], fz = (float)S.snap.f[2];
+            const float sx = (float)S.snap.s[0], sy = (float)S.snap.s[1], sz = (float)S.snap.s[2];
+            const float ux = (float)S.snap.u[0], uy = (float)S.snap.u[1], uz = (float)S.snap.u[2];
+            const int rx0 = S.snap.rx0, ry0 = S.snap.ry0, rnx = S.snap.rnx;
             const int local = (int)(task - __ldg(tileOffset + si));
             const int tpx0 = (rx0 + local % rnx) * kTile, tpy0 = (ry0 + local / rnx) * kTile;
             // ---- tile state ----
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
             while (more) {
                 const BvhNode* np = sc.nodes + node;
                 const float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
+                myNodes++;
                 // this lane's child box, relative to the eye
                 const float bx0 = (second ? q1.z : q0.x) - ox, by0 = (second ? q1.w : q0.y) - oy, bz0 = (second ? q2.x : q0.z) - oz;
                 const float bx1 = (second ? q2.y : q0.w) - ox, by1 = (second ? q2.z : q1.x) - oy, bz1 = (second ? q2.w : q1.y) - oz;
@@ -280,7 +286,8 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
                     const int code = ~l;
                     const int first = code >> kLeafShift, cnt = code & kLeafMask;
                     __syncwarp();
-                    if (lane < cnt) setup_triangle(sc, snaps + si, first + lane, S.tri[lane], ox, oy, oz, zNear, zcull);
+                    myTris += cnt;
+                    if (lane < cnt) setup_triangle(sc, &S.snap, first + lane, S.tri[lane], ox, oy, oz, zNear, zcull);
                     __syncwarp();
                     bool dirty = false;
                     for (int k = 0; k < cnt; ++k) {
@@ -365,17 +372,23 @@ __global__ void __launch_bounds__(kVisThreads) k_visibility(DeviceScene sc, Came
                 const int id = S.id[k * 32 + lane];
                 const int left = __shfl_up_sync(0xffffffffu, id, 1), up = __shfl_up_sync(0xffffffffu, id, 8);
                 const bool dupe = ((lane & 7) != 0 && left == id) || (lane >= 8 && up == id);
-                if (id != kNoId && !dupe) flags[(size_t)slot * sc.Tpad + id] = 1;
+                if (id != kNoId && !dupe) flags[(size_t)S.snap.slot * sc.Tpad + id] = 1;
                 if (idImage) {
                     const int px = tpx0 + (k & 3) * 8 + (lane & 7), py = tpy0 + (k >> 2) * 4 + (lane >> 3);
                     if (px < cam.W && py < cam.H) idImage[(size_t)py * cam.W + px] = id == kNoId ? -1 : id;
                 }
             }
             if (lane == 0) myRays += (unsigned long long)(vw * vh);
+            myTiles++;
             __syncwarp();
         }
     }
-    if (lane == 0 && myRays) atomicAdd(&counters[0], myRays);
+    if (lane == 0 && myRays) {
+        atomicAdd(&counters[0], myRays);
+        atomicAdd(&counters[2], (unsigned long long)myNodes);
+        atomicAdd(&counters[3], (unsigned long long)myTris);
+        atomicAdd(&counters[4], (unsigned long long)myTiles);
+    }
 }
 
 // flags [slot][Tpad] bytes (0/1) -> bitmap row words; thread = one word = 32 flag bytes; clears the flags
