@@ -33,6 +33,7 @@ constexpr int kTilePixels = kTile * kTile;
 constexpr int kNoId = 0x7fffffff;
 constexpr float kDepthTie = 1.0f + 1.0f / 65536.0f;
 constexpr int kTriWords = 16;   // floats per staged triangle
+constexpr int kPending = 32;    // triangles staged together (one per lane)
 
 struct Hit {
     float t;
@@ -117,7 +118,7 @@ __device__ __forceinline__ float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1
 struct WarpShared {
     float t[kTilePixels];            // nearest depth per ray, index = block * 32 + lane (block = 8x4 pixels)
     int id[kTilePixels];             // its triangle
-    float tri[kLeafMax][kTriWords];  // staged leaf triangles
+    float tri[kPending][kTriWords];  // staged triangles
     int stack[2 * kMaxDepth];        // (link, zmin bits) pairs
     Snapshot snap;                   // the camera pose of the current tile
 };
@@ -261,36 +262,21 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
             __syncwarp();
 
             // ---- frustum-packet traversal ----
+            // Leaf triangles are not tested one leaf at a time: they queue up (lane l holds the l-th pending triangle) until the
+            // queue could overflow at the next node, then all pending triangles are set up in parallel, one per lane (the fp64
+            // setup then runs on up to 32 lanes instead of <= 8), and tested one after the other.
             int sp_ = 0;
             int node = 0;
             bool more = sc.T > 0;
-            while (more) {
-                const BvhNode* np = sc.nodes + node;
-                const float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
-                myNodes++;
-                // this lane's child box, relative to the eye
-                const float bx0 = (second ? q1.z : q0.x) - ox, by0 = (second ? q1.w : q0.y) - oy, bz0 = (second ? q2.x : q0.z) - oz;
-                const float bx1 = (second ? q2.y : q0.w) - ox, by1 = (second ? q2.z : q1.x) - oy, bz1 = (second ? q2.w : q1.y) - oz;
-                // maximum of n.P over the box
-                const float m = (nx >= 0.f ? bx1 : bx0) * nx + (ny >= 0.f ? by1 : by0) * ny + (nz >= 0.f ? bz1 : bz0) * nz;
-                const float limit = role == 5 ? -(zcull * 1.000001f + 1e-4f) : thr;
-                const unsigned ok = __ballot_sync(0xffffffffu, m >= limit);
-                const bool h0 = (ok & 0x3fu) == 0x3fu, h1 = (ok & 0xfc0u) == 0xfc0u;
-                const float zmin0 = -__shfl_sync(0xffffffffu, m, 5), zmin1 = -__shfl_sync(0xffffffffu, m, 11);
-                const int l0 = __float_as_int(q3.x), l1 = __float_as_int(q3.y);
-                // ---- leaves ----
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int l = c ? l1 : l0;
-                    if (!(c ? h1 : h0) || l >= 0) continue;
-                    const int code = ~l;
-                    const int first = code >> kLeafShift, cnt = code & kLeafMask;
+            int pend = 0, myTri = 0;
+            for (;;) {
+                if (pend > kPending - 2 * kLeafMax || (!more && pend > 0)) {
+                    // ---- flush the pending triangles ----
                     __syncwarp();
-                    myTris += cnt;
-                    if (lane < cnt) setup_triangle(sc, &S.snap, first + lane, S.tri[lane], ox, oy, oz, zNear, zcull);
+                    if (lane < pend) setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull);
                     __syncwarp();
                     bool dirty = false;
-                    for (int k = 0; k < cnt; ++k) {
+                    for (int k = 0; k < pend; ++k) {
                         const float* tr = S.tri[k];
                         const float zloTri = tr[15];
                         if (zloTri < 0.f || zloTri > zcull) continue;
@@ -323,6 +309,7 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                             }
                         }
                     }
+                    pend = 0;
                     if (__any_sync(0xffffffffu, dirty)) {
                         // hierarchical depth culling: lane b takes the farthest hit of block b (conflict-free diagonal walk);
                         // rays without a hit still hold zFar, rays outside the image hold 0
@@ -335,6 +322,31 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                         for (int o2 = 16; o2; o2 >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o2));
                         zcull = zm;
                     }
+                }
+                if (!more) break;
+                const BvhNode* np = sc.nodes + node;
+                const float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
+                myNodes++;
+                // this lane's child box, relative to the eye
+                const float bx0 = (second ? q1.z : q0.x) - ox, by0 = (second ? q1.w : q0.y) - oy, bz0 = (second ? q2.x : q0.z) - oz;
+                const float bx1 = (second ? q2.y : q0.w) - ox, by1 = (second ? q2.z : q1.x) - oy, bz1 = (second ? q2.w : q1.y) - oz;
+                // maximum of n.P over the box
+                const float m = (nx >= 0.f ? bx1 : bx0) * nx + (ny >= 0.f ? by1 : by0) * ny + (nz >= 0.f ? bz1 : bz0) * nz;
+                const float limit = role == 5 ? -(zcull * 1.000001f + 1e-4f) : thr;
+                const unsigned ok = __ballot_sync(0xffffffffu, m >= limit);
+                const bool h0 = (ok & 0x3fu) == 0x3fu, h1 = (ok & 0xfc0u) == 0xfc0u;
+                const float zmin0 = -__shfl_sync(0xffffffffu, m, 5), zmin1 = -__shfl_sync(0xffffffffu, m, 11);
+                const int l0 = __float_as_int(q3.x), l1 = __float_as_int(q3.y);
+                // ---- leaves: queue their triangles ----
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int l = c ? l1 : l0;
+                    if (!(c ? h1 : h0) || l >= 0) continue;
+                    const int code = ~l;
+                    const int first = code >> kLeafShift, cnt = code & kLeafMask;
+                    if (lane >= pend && lane < pend + cnt) myTri = first + lane - pend;
+                    pend += cnt;
+                    myTris += cnt;
                 }
                 // ---- inner children: nearer one first ----
                 const bool i0 = h0 && l0 >= 0, i1 = h1 && l1 >= 0;
