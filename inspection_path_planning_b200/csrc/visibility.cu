@@ -130,8 +130,9 @@ struct WarpShared {
 // >= 0 and det > 0.  Setup runs in fp64 from the exact fp32 vertices, the fp32 eye and the fp64 camera basis; only the final
 // coefficients are rounded to fp32 (in fp32 the normal of an edge that points at the camera, |A' x e| << |A'||e|, lost up to
 // 0.03 pixel).
-__device__ __forceinline__ void setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
-                                               float oy, float oz, float zNear, float zcull) {
+__device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
+                                               float oy, float oz, float zNear, float zcull, float tXmin, float tXmax, float tYmin,
+                                               float tYmax) {
     const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
     float valid = -1.f;
     if (b.w == 0.f) {  // not degenerate
@@ -163,9 +164,16 @@ __device__ __forceinline__ void setup_triangle(const DeviceScene& sc, const Snap
             o[9] = sg * (float)ddot(ngx, ngy, ngz, fX, fY, fZ); o[10] = sg * (float)ddot(ngx, ngy, ngz, sX, sY, sZ); o[11] = sg * (float)ddot(ngx, ngy, ngz, uX, uY, uZ);
             o[12] = sg * (float)vol;
             o[13] = a.w;  // triangle id (int bits)
+            // can any pixel centre of the tile be inside?  Each edge function is monotone in X and in Y (also as computed), so its
+            // value at the extreme pixel centre of the tile bounds it over the tile.
+            const float ma = __fmaf_rn(o[1], o[1] >= 0.f ? tXmax : tXmin, __fmaf_rn(o[2], o[2] >= 0.f ? tYmax : tYmin, o[0]));
+            const float mb = __fmaf_rn(o[4], o[4] >= 0.f ? tXmax : tXmin, __fmaf_rn(o[5], o[5] >= 0.f ? tYmax : tYmin, o[3]));
+            const float mc = __fmaf_rn(o[7], o[7] >= 0.f ? tXmax : tXmin, __fmaf_rn(o[8], o[8] >= 0.f ? tYmax : tYmin, o[6]));
+            if (fminf(fminf(ma, mb), mc) < 0.f) valid = -1.f;
         }
     }
     o[15] = valid;
+    return valid >= 0.f;
 }
 
 // last index s in [0, nSnaps) with tileOffset[s] <= task (tileOffset[0] == 0): 32-ary search, one probe per lane and round
@@ -256,7 +264,9 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
             // expression is used for a pixel whatever triangle is tested, so shared edges stay watertight.
             const float Xl = __fmaf_rn((float)(tpx0 + (lane & 7)), kx, cx), Yl = __fmaf_rn((float)(tpy0 + (lane >> 3)), ky, cy);
             const float kx8 = 8.f * kx, ky4 = 4.f * ky;
-            // extreme pixel centres of block b = lane, by the same expressions its corner pixels use
+            // extreme pixel centres of the tile and of block b = lane, by the same expressions the corner pixels use
+            const float tXmin = __fmaf_rn((float)tpx0, kx, cx), tXmax = __fmaf_rn(3.f, kx8, __fmaf_rn((float)(tpx0 + 7), kx, cx));
+            const float tYmin = __fmaf_rn((float)tpy0, ky, cy), tYmax = __fmaf_rn(7.f, ky4, __fmaf_rn((float)(tpy0 + 3), ky, cy));
             const float bXmin = __fmaf_rn((float)(lane & 3), kx8, __fmaf_rn((float)tpx0, kx, cx)), bXmax = __fmaf_rn((float)(lane & 3), kx8, __fmaf_rn((float)(tpx0 + 7), kx, cx));
             const float bYmin = __fmaf_rn((float)(lane >> 2), ky4, __fmaf_rn((float)tpy0, ky, cy)), bYmax = __fmaf_rn((float)(lane >> 2), ky4, __fmaf_rn((float)(tpy0 + 3), ky, cy));
             __syncwarp();
@@ -273,13 +283,16 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                 if (pend > kPending - 2 * kLeafMax || (!more && pend > 0)) {
                     // ---- flush the pending triangles ----
                     __syncwarp();
-                    if (lane < pend) setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull);
-                    __syncwarp();
+                    bool mine = false;
+                    if (lane < pend) mine = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tXmin, tXmax, tYmin, tYmax);
+                    unsigned live = __ballot_sync(0xffffffffu, mine);  // triangles that can produce a fragment in this tile
                     bool dirty = false;
-                    for (int k = 0; k < pend; ++k) {
+                    while (live) {
+                        const int k = __ffs(live) - 1;
+                        live &= live - 1;
                         const float* tr = S.tri[k];
                         const float zloTri = tr[15];
-                        if (zloTri < 0.f || zloTri > zcull) continue;
+                        if (zloTri > zcull) continue;
                         const float eaf = tr[0], eas = tr[1], eau = tr[2], ebf = tr[3], ebs = tr[4], ebu = tr[5], ecf = tr[6], ecs = tr[7],
                                     ecu = tr[8], gf = tr[9], gs = tr[10], gu = tr[11], vol = tr[12];
                         const int id = __float_as_int(tr[13]);
