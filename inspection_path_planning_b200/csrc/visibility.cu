@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
             int node = 0;
             bool more = sc.T > 0;
             int pend = 0, myTri = 0;
+            bool tileHit = false;  // some ray of the tile has a hit
             for (;;) {
                 if (pend > kPending - 2 * kLeafMax || (!more && pend > 0)) {
                     // ---- flush the pending triangles ----
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                     }
                     pend = 0;
                     if (__any_sync(0xffffffffu, dirty)) {
+                        tileHit = true;
                         // hierarchical depth culling: lane b takes the farthest hit of block b (conflict-free diagonal walk);
                         // rays without a hit still hold zFar, rays outside the image hold 0
                         __syncwarp();
@@ -368,6 +370,8 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                     if (lane == 0) {
                         S.stack[2 * sp_] = swap ? l0 : l1;
                         S.stack[2 * sp_ + 1] = __float_as_int(swap ? zmin0 : zmin1);
+                        // the far child is visited later: start pulling its node towards L1 now
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.nodes + (swap ? l0 : l1)));
                     }
                     sp_++;
                     node = swap ? l1 : l0;
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
             }
             __syncwarp();
             // ---- the winners: one byte store per run of equal ids inside an 8x4 block ----
+            if (tileHit || idImage)
 #pragma unroll 4
             for (int k = 0; k < kTilePixels / 32; ++k) {
                 const int id = S.id[k * 32 + lane];

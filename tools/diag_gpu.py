@@ -24,12 +24,16 @@ plans = cpp_binding.pack_population(random_plans(rng, g.getNumberOfBoxes(), pop,
 names = ["reduce", "visibility", "collision", "pack", "plan"]
 for it in range(3):
     g.counters(reset=True)
+    g.visibility_stats(reset=True)
     for k in range(5):
         g.kernel_time(k, reset=True)
     t = time.time()
     fit = g.evaluatePopulation(plans, True, True)
     dt = time.time() - t
     c = g.counters()
+    vs = g.visibility_stats()
+    if vs["tiles"]:
+        print("   per tile: nodes %.1f triangles %.1f (tiles %d)" % (vs["nodes"] / vs["tiles"], vs["triangles"] / vs["tiles"], vs["tiles"]), flush=True)
     kt = {names[k]: g.kernel_time(k) for k in range(5)}
     print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  counters %s" % (it, dt, pop / dt, (1 - fit[:, 0]).mean(), c), flush=True)
     print("   kernel ms:", {k: (round(v[0], 3), v[1]) for k, v in kt.items()}, flush=True)
