@@ -123,6 +123,10 @@ int ipp_edges_collide(ipp_t* h, const double* edges_nx6, int64_t n, uint8_t* out
 int ipp_boxes_hit_mesh(ipp_t* h, const double* centres_nx3, int64_t n, double half_side, uint8_t* out_flags);
 /* one camera pose -> per-pixel nearest triangle id (-1 background), row-major [y][x] */
 int ipp_render_ids(ipp_t* h, const double* eye3, const double* center3, const double* up3, int32_t* out_HxW);
+/* the depth-sorted leaf table the binned visibility kernel builds for one camera pose: up to cap packed entries
+ * [depth:16 | tx0:5 tx1:5 ty0:5 ty1:5 | first triangle:24 count:4], *count = entries of the pose, out_tile_mask32 = occupied tiles */
+int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,
+                   uint32_t* out_tile_mask32);
 /* BVH self-check: closest-hit of n rays (origin xyz, dir xyz) through the BVH and by brute force; returns
  * the number of mismatching ids */
 int ipp_bvh_selftest(ipp_t* h, const float* rays_nx6, int64_t n, int32_t* out_ids, int64_t* mismatches);
@@ -146,11 +150,16 @@ int ipp_flush_l2(ipp_t* h);
 /* counters since the last reset: [0] kernel launches, [1] pixel-centre rays issued, [2] snapshots rendered,
  * [3] edges rendered, [4] collision queries, [5] plan_reduce launches, [6] plans reduced, [7] bitmap rows read */
 int ipp_counters(ipp_t* h, int64_t* out8, int reset);
-/* traversal statistics of the edge-visibility kernel since the last reset (reset by ipp_counters too):
- * [0] BVH nodes fetched (64 B each), [1] triangles staged (48 B each), [2] 32x32-pixel tiles, [3] pixel-centre rays */
+/* statistics of the edge-visibility kernel since the last reset (reset by ipp_counters too):
+ * [0] acceleration-structure data fetched in 64-byte units (BVH nodes of the tile-walking variant, 8 leaf-bin entries of the
+ * binned variant), [1] triangles staged (48 B each), [2] 32x32-pixel tiles rasterised, [3] pixel-centre rays */
 int ipp_visibility_stats(ipp_t* h, int64_t* out4, int reset);
+/* which edge-visibility kernel renders the item buffers: 1 = depth-sorted leaf bins per 128x128 supertile (the default when the
+ * mesh has <= 16384 BVH leaves and the image is <= 1024 pixels a side), 0 = BVH frustum walk per tile.  Same sampling rule and
+ * rasteriser either way.  *out_active (nullable) receives the variant in force after the call; use_bins < 0 only queries. */
+int ipp_visibility_variant(ipp_t* h, int use_bins, int* out_active);
 /* accumulated CUDA-event time of a named kernel group since the last reset:
- * 0 = plan_reduce, 1 = edge_visibility, 2 = edge_collision, 3 = pack, 4 = energy+mark */
+ * 0 = plan_reduce, 1 = edge_visibility, 2 = edge_collision, 3 = pack, 4 = energy+mark, 5 = leaf tables of the binned variant */
 int ipp_kernel_time(ipp_t* h, int which, double* ms, int64_t* launches, int reset);
 int ipp_set_profiling(ipp_t* h, int on);
 

@@ -26,6 +26,7 @@ UNITS = [
     ("evaluator.cu", ["-fmad=false"]),
     ("lbvh.cu", []),
     ("visibility.cu", []),
+    ("visibility_bins.cu", []),
     ("comm.cu", []),
     ("ipp_api.cu", []),
     ("mesh_io.cpp", []),

@@ -256,6 +256,20 @@ class PlanCoverageEstimator(object):
         _lib.check(self._L.ipp_bvh_selftest(self._h, r.ctypes.data_as(_lib.c_f32p), r.shape[0], ids.ctypes.data_as(_lib.c_i32p), C.byref(mism)))
         return ids, int(mism.value)
 
+    def leaf_table(self, eye, center, up=(0.0, 0.0, 1.0), cap=16384):
+        """Depth-sorted leaf table of one camera pose (binned visibility kernel): dict of numpy arrays + the 32-row tile mask."""
+        e, c, u = (np.ascontiguousarray(v, dtype=np.float64) for v in (eye, center, up))
+        out = np.zeros(cap, dtype=np.uint64)
+        mask = np.zeros(32, dtype=np.uint32)
+        n = C.c_int64()
+        _lib.check(self._L.ipp_leaf_table(self._h, e.ctypes.data_as(_lib.c_f64p), c.ctypes.data_as(_lib.c_f64p), u.ctypes.data_as(_lib.c_f64p),
+                                          out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n), mask.ctypes.data_as(_lib.c_u32p)))
+        k = out[:min(int(n.value), cap)]
+        return {"count": int(n.value), "zq": (k >> np.uint64(48)).astype(np.int64), "tx0": ((k >> np.uint64(43)) & np.uint64(31)).astype(np.int64),
+                "tx1": ((k >> np.uint64(38)) & np.uint64(31)).astype(np.int64), "ty0": ((k >> np.uint64(33)) & np.uint64(31)).astype(np.int64),
+                "ty1": ((k >> np.uint64(28)) & np.uint64(31)).astype(np.int64), "first": ((k >> np.uint64(4)) & np.uint64(0xFFFFFF)).astype(np.int64),
+                "cnt": (k & np.uint64(15)).astype(np.int64), "tile_mask": mask}
+
     def bvh_selftest_ex(self, rays):
         r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
         ids = np.zeros(r.shape[0], dtype=np.int32)
@@ -280,6 +294,12 @@ class PlanCoverageEstimator(object):
         out = np.zeros(4, dtype=np.int64)
         _lib.check(self._L.ipp_visibility_stats(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
         return dict(zip(["nodes", "triangles", "tiles", "rays"], (int(x) for x in out)))
+
+    def visibility_variant(self, use_bins=None):
+        """Selects (True / False) or queries (None) the edge-visibility kernel: leaf bins or BVH walk per tile."""
+        out = C.c_int()
+        _lib.check(self._L.ipp_visibility_variant(self._h, -1 if use_bins is None else int(bool(use_bins)), C.byref(out)))
+        return "bins" if out.value else "bvh"
 
     def kernel_time(self, which, reset=False):
         ms, n = C.c_double(), C.c_int64()

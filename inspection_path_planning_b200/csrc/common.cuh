@@ -54,6 +54,9 @@ struct DeviceScene {
     // BVH-ordered triangles, file vertex order (exact collision predicate); a.w = original id
     float4 *oa = nullptr, *ob = nullptr, *oc = nullptr;
     BvhNode* nodes = nullptr;
+    // the leaves of the BVH as a flat table (node order = Morton order): padded box, leafLo.w = (first << kLeafShift) | count as int bits
+    float4 *leafLo = nullptr, *leafHi = nullptr;
+    int nLeaves = 0;
     double* area = nullptr;   // [areaPad] file order, zero padded to a multiple of kTileTris
     float bbmin[3], bbmax[3]; // float bounding box of all vertices
 };

@@ -150,6 +150,24 @@ Evaluator::Evaluator(const std::string& scenePath, const double specs[8], bool p
         rowCapacity_ = std::min<int64_t>(nKeys_, budget / (rowWords_ * 4));
         if (rowCapacity_ < 1) throw std::runtime_error("libipp: not enough device memory for the edge-bitmap cache");
     }
+    // K4 variant and the per-batch snapshot budget of its leaf tables
+    useBins_ = bins_supported(scene_, cam_);
+    if (const char* e = getenv("IPP_VISIBILITY")) {
+        if (std::string(e) == "bvh") useBins_ = false;
+    }
+    {
+        size_t freeB = 0, totalB = 0;
+        IPP_CUDA_CHECK(cudaMemGetInfo(&freeB, &totalB));
+        const int64_t tilesPerImage = (int64_t)((cam_.W + 31) / 32) * ((cam_.H + 31) / 32);
+        maxSnapsPerBatch_ = std::max<int64_t>(64, ((int64_t)1 << 30) / std::max<int64_t>(1, tilesPerImage));
+        bins_.stride = bins_table_stride(scene_.nLeaves);
+        bins_.gridBlocks = bins_grid_blocks();
+        if (useBins_) {
+            const int64_t tableBudget = std::min<int64_t>((int64_t)16 << 30, (int64_t)(freeB * 0.10));
+            maxSnapsPerBatch_ = std::max<int64_t>(64, std::min<int64_t>(maxSnapsPerBatch_, tableBudget / ((int64_t)bins_.stride * 8)));
+        }
+    }
+    d_countsAll_ = dalloc<int>(nKeys_ + 1);
     d_rows_ = dalloc<uint32_t>((size_t)(rowCapacity_ + 1) * rowWords_);
     d_freeStack_ = dalloc<int>(rowCapacity_);
     d_flags_ = dalloc<uint8_t>((size_t)batchCap_ * scene_.Tpad);
@@ -195,6 +213,8 @@ Evaluator::~Evaluator() {
     cudaFree(d_flags_); cudaFree(d_rowOfSlot_); cudaFree(d_counts_); cudaFree(d_snapOffset_);
     cudaFree(d_snaps_); cudaFree(d_ntiles_); cudaFree(d_tileOffset_); cudaFree(d_scanTmp_);
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
+    cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
+    cudaFree(bins_.scratch); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
     cudaFree(d_ids_); cudaFree(d_offsets_); cudaFree(d_fitness_); cudaFree(d_active_); cudaFree(d_union_);
     cudaFree(d_flushBuf_);
     for (auto& e : pendingEv_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -280,7 +300,8 @@ void Evaluator::visibilityStats(int64_t out[4], bool reset) {
     unsigned long long c[8];
     IPP_CUDA_CHECK(cudaMemcpyAsync(c, d_visCounters_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
     sync();
-    out[0] = (int64_t)c[2]; out[1] = (int64_t)c[3]; out[2] = (int64_t)c[4]; out[3] = (int64_t)c[0];
+    // out[0]: 64-byte units of acceleration-structure data fetched = BVH nodes (visibility.cu) + 8-byte bin entries / 8 (visibility_bins.cu)
+    out[0] = (int64_t)c[2] + (int64_t)(c[5] / 8); out[1] = (int64_t)c[3]; out[2] = (int64_t)c[4]; out[3] = (int64_t)c[0];
     if (reset) IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
 }
 void Evaluator::timerStart() {
@@ -335,10 +356,66 @@ void Evaluator::ensureSnapBuffers(int64_t nSnaps) {
         cudaFree(d_snaps_);
         cudaFree(d_ntiles_);
         cudaFree(d_tileOffset_);
-        snapCap_ = nSnaps + nSnaps / 4 + 64;
+        snapCap_ = std::min<int64_t>(nSnaps + nSnaps / 4 + 64, std::max<int64_t>(maxSnapsPerBatch_, nSnaps) + 1);
         d_snaps_ = dalloc<Snapshot>(snapCap_);
         d_ntiles_ = dalloc<int>(snapCap_);
         d_tileOffset_ = dalloc<int>(snapCap_);
+        if (useBins_) {
+            cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
+            cudaFree(d_superOffset_);
+            bins_.table = dalloc<unsigned long long>((size_t)snapCap_ * bins_.stride);
+            bins_.tableCount = dalloc<int>(snapCap_);
+            bins_.tileMask = dalloc<uint32_t>((size_t)snapCap_ * 32);
+            bins_.superMask = dalloc<unsigned long long>(snapCap_);
+            bins_.nSuper = dalloc<int>(snapCap_);
+            d_superOffset_ = dalloc<int>(snapCap_);
+        }
+    }
+    if (useBins_ && !bins_.scratch)
+        bins_.scratch = dalloc<unsigned long long>((size_t)bins_.gridBlocks * bins_warps_per_block() * bins_.stride);
+}
+
+void Evaluator::setUseBins(bool on) {
+    bind();
+    sync();
+    on = on && bins_supported(scene_, cam_);
+    if (on == useBins_) return;
+    useBins_ = on;
+    snapCap_ = 0;  // buffers are re-made for the variant on the next batch
+}
+
+// K4 for the nSnaps camera poses in d_snaps_ (either variant); d_idImage: test hook
+void Evaluator::renderSnapshots(int nSnaps, int32_t* d_idImage) {
+    if (useBins_) {
+        groupBegin(KG_TABLE);
+        launch_leaf_table(scene_, cam_, d_snaps_, nSnaps, bins_, stream_);
+        groupEnd(KG_TABLE);
+        if (d_idImage) {
+            // test hook: every supertile of the image is scheduled so that background pixels are reported too
+            const int nsx = (cam_.W + 127) / 128, nsy = (cam_.H + 127) / 128;
+            unsigned long long m = 0;
+            for (int y = 0; y < nsy; ++y)
+                for (int x = 0; x < nsx; ++x) m |= 1ull << (y * 8 + x);
+            int cnt = nsx * nsy;
+            IPP_CUDA_CHECK(cudaMemcpyAsync(bins_.superMask, &m, sizeof(m), cudaMemcpyHostToDevice, stream_));
+            IPP_CUDA_CHECK(cudaMemcpyAsync(bins_.nSuper, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, stream_));
+            sync();
+        }
+        IPP_CUDA_CHECK(cudaMemsetAsync(bins_.nSuper + nSnaps, 0, sizeof(int), stream_));
+        exclusiveScan(bins_.nSuper, d_superOffset_, nSnaps + 1);
+        int totalSuper = readInt(d_superOffset_ + nSnaps);
+        groupBegin(KG_VISIBILITY);
+        launch_visibility_bins(scene_, cam_, d_snaps_, d_superOffset_, nSnaps, totalSuper, bins_, d_flags_, d_idImage, d_visCounters_, stream_);
+        groupEnd(KG_VISIBILITY);
+        nLaunches_ += 3;
+    } else {
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_ntiles_ + nSnaps, 0, sizeof(int), stream_));
+        exclusiveScan(d_ntiles_, d_tileOffset_, nSnaps + 1);
+        int totalTiles = readInt(d_tileOffset_ + nSnaps);
+        groupBegin(KG_VISIBILITY);
+        launch_visibility(scene_, cam_, d_snaps_, d_tileOffset_, nSnaps, totalTiles, d_flags_, d_idImage, d_visCounters_, stream_);
+        groupEnd(KG_VISIBILITY);
+        nLaunches_ += 2;
     }
 }
 
@@ -368,23 +445,25 @@ void Evaluator::renderBatch(const int* d_keys, const float* d_angles, int n, con
     groupBegin(KG_PLAN);
     launch_fill_snapshots(d_keys, d_angles, n, d_pos_, N_, sceneCenter_, cam_, scene_, d_snapOffset_, d_snaps_, d_ntiles_, stream_);
     groupEnd(KG_PLAN);
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_ntiles_ + nSnaps, 0, sizeof(int), stream_));
-    exclusiveScan(d_ntiles_, d_tileOffset_, nSnaps + 1);
-    int totalTiles = readInt(d_tileOffset_ + nSnaps);
-    groupBegin(KG_VISIBILITY);
-    launch_visibility(scene_, cam_, d_snaps_, d_tileOffset_, nSnaps, totalTiles, d_flags_, nullptr, d_visCounters_, stream_);
-    groupEnd(KG_VISIBILITY);
+    renderSnapshots(nSnaps, nullptr);
     groupBegin(KG_PACK);
     launch_pack_rows(d_flags_, n, scene_.Tpad, d_rowOfSlot, d_rows_, rowWords_, stream_);
     groupEnd(KG_PACK);
-    nLaunches_ += 5;
+    nLaunches_ += 3;
     nSnapshots_ += nSnaps;
     nEdgesRendered_ += n;
 }
 
 void Evaluator::renderNewEdges(int nNew, const float* d_angles) {
-    for (int b0 = 0; b0 < nNew; b0 += batchCap_) {
-        int n = std::min(batchCap_, nNew - b0);
+    // camera poses per edge, so that a batch respects both the flag rows and the pose budget (leaf tables, int32 work offsets)
+    std::vector<int> perEdge(nNew);
+    launch_count_snapshots(d_newKeys_, nNew, d_pos_, N_, cam_, d_countsAll_, stream_);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(perEdge.data(), d_countsAll_, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    nLaunches_++;
+    for (int b0 = 0, n = 0; b0 < nNew; b0 += n) {
+        int64_t snaps = 0;
+        for (n = 0; b0 + n < nNew && n < batchCap_ && (n == 0 || snaps + perEdge[b0 + n] <= maxSnapsPerBatch_); ++n) snaps += perEdge[b0 + n];
         launch_assign_rows(d_newKeys_ + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
         renderBatch(d_newKeys_ + b0, d_angles ? d_angles + b0 : nullptr, n, d_rowOfSlot_);
         launch_publish_rows(d_newKeys_ + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
@@ -616,17 +695,30 @@ void Evaluator::renderIds(const double* eye, const double* center, const double*
     ensureSnapBuffers(2);
     int32_t* d_img = dalloc<int32_t>((size_t)cam_.W * cam_.H);
     launch_single_snapshot(d_snaps_, eye, center, up, cam_, scene_, d_ntiles_, stream_);
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_ntiles_ + 1, 0, sizeof(int), stream_));
-    exclusiveScan(d_ntiles_, d_tileOffset_, 2);
-    int totalTiles = readInt(d_tileOffset_ + 1);
-    launch_visibility(scene_, cam_, d_snaps_, d_tileOffset_, 1, totalTiles, d_flags_, d_img, d_visCounters_, stream_);
+    renderSnapshots(1, d_img);
     int scratch = (int)rowCapacity_;
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowOfSlot_, &scratch, sizeof(int), cudaMemcpyHostToDevice, stream_));
     launch_pack_rows(d_flags_, 1, scene_.Tpad, d_rowOfSlot_, d_rows_, rowWords_, stream_);  // clears the flags
-    nLaunches_ += 4;
+    nLaunches_ += 2;
     IPP_CUDA_CHECK(cudaMemcpyAsync(out, d_img, (size_t)cam_.W * cam_.H * 4, cudaMemcpyDeviceToHost, stream_));
     sync();
     cudaFree(d_img);
+}
+
+void Evaluator::leafTable(const double* eye, const double* center, const double* up, uint64_t* out, int64_t cap, int64_t* count,
+                          uint32_t* mask32) {
+    bind();
+    if (!useBins_) throw std::logic_error("libipp: the leaf-bin variant is not in force for this evaluator");
+    ensureSnapBuffers(2);
+    launch_single_snapshot(d_snaps_, eye, center, up, cam_, scene_, d_ntiles_, stream_);
+    launch_leaf_table(scene_, cam_, d_snaps_, 1, bins_, stream_);
+    nLaunches_ += 2;
+    int n = readInt(bins_.tableCount);
+    *count = n;
+    int64_t m = std::min<int64_t>(n, cap);
+    if (m > 0) IPP_CUDA_CHECK(cudaMemcpyAsync(out, bins_.table, (size_t)m * 8, cudaMemcpyDeviceToHost, stream_));
+    if (mask32) IPP_CUDA_CHECK(cudaMemcpyAsync(mask32, bins_.tileMask, 32 * 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
 }
 
 void Evaluator::bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute, float* outT) {

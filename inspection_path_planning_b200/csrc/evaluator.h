@@ -8,13 +8,14 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels.h"
 #include "planner.h"
 
 namespace ipp {
 
 struct Comm;  // comm.cpp
 
-enum KernelGroup { KG_REDUCE = 0, KG_VISIBILITY = 1, KG_COLLISION = 2, KG_PACK = 3, KG_PLAN = 4, KG_COUNT = 5 };
+enum KernelGroup { KG_REDUCE = 0, KG_VISIBILITY = 1, KG_COLLISION = 2, KG_PACK = 3, KG_PLAN = 4, KG_TABLE = 5, KG_COUNT = 6 };
 
 class Evaluator {
    public:
@@ -42,6 +43,7 @@ class Evaluator {
     void edgesCollide(const double* edges, int64_t n, uint8_t* out);
     void boxesHitMesh(const double* centres, int64_t n, double half, uint8_t* out);
     void renderIds(const double* eye, const double* center, const double* up, int32_t* out);
+    void leafTable(const double* eye, const double* center, const double* up, uint64_t* out, int64_t cap, int64_t* count, uint32_t* mask32);
     void bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute = nullptr, float* outT = nullptr);
 
     // ---- plumbing ----
@@ -53,6 +55,8 @@ class Evaluator {
     void visibilityStats(int64_t out[4], bool reset);
     void kernelTime(int which, double* ms, int64_t* launches, bool reset);
     void setProfiling(bool on) { profiling_ = on; }
+    bool usesBins() const { return useBins_; }
+    void setUseBins(bool on);  // K4 variant: leaf bins (default when supported) or BVH walk per tile
     cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
     void bind() const { IPP_CUDA_CHECK(cudaSetDevice(device_)); }
@@ -71,6 +75,7 @@ class Evaluator {
    private:
     void renderNewEdges(int nNew, const float* d_angles);
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
+    void renderSnapshots(int nSnaps, int32_t* d_idImage);
     void ensurePlanBuffers(int64_t pop, int64_t nGenes);
     void ensureSnapBuffers(int64_t nSnaps);
     int readInt(const int* d);
@@ -111,7 +116,13 @@ class Evaluator {
     int64_t snapCap_ = 0;
     void* d_scanTmp_ = nullptr;
     size_t scanTmpBytes_ = 0;
-    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] tile cursor, [2] nodes fetched, [3] triangles staged, [4] tiles
+    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] work cursor, [2] nodes fetched, [3] triangles staged, [4] tiles, [5] bin entries read
+    // leaf-bin variant of K4 (visibility_bins.cu)
+    bool useBins_ = false;
+    BinBuffers bins_;
+    int* d_superOffset_ = nullptr;
+    int* d_countsAll_ = nullptr;  // snapshots per new edge (nKeys + 1)
+    int64_t maxSnapsPerBatch_ = 1 << 20;
     float* d_angleOne_ = nullptr;
 
     // plan buffers (host-pointer entry point)
@@ -126,8 +137,8 @@ class Evaluator {
     cudaEvent_t evStart_ = nullptr, evStop_ = nullptr;
     struct EvPair { cudaEvent_t a, b; int group; };
     std::vector<EvPair> pendingEv_, freeEv_;
-    double groupMs_[KG_COUNT] = {0, 0, 0, 0, 0};
-    int64_t groupLaunches_[KG_COUNT] = {0, 0, 0, 0, 0};
+    double groupMs_[KG_COUNT] = {0, 0, 0, 0, 0, 0};
+    int64_t groupLaunches_[KG_COUNT] = {0, 0, 0, 0, 0, 0};
     bool profiling_ = true;
     uint32_t* d_flushBuf_ = nullptr;
     int64_t flushWords_ = 0;

@@ -269,6 +269,18 @@ int ipp_visibility_stats(ipp_t* h, int64_t* out4, int reset) {
     E(h).visibilityStats(out4, reset != 0);
     IPP_CATCH
 }
+int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,
+                   uint32_t* out_tile_mask32) {
+    IPP_TRY
+    E(h).leafTable(eye3, center3, up3, out, cap, count, out_tile_mask32);
+    IPP_CATCH
+}
+int ipp_visibility_variant(ipp_t* h, int use_bins, int* out_active) {
+    IPP_TRY
+    if (use_bins >= 0) E(h).setUseBins(use_bins != 0);
+    if (out_active) *out_active = E(h).usesBins() ? 1 : 0;
+    IPP_CATCH
+}
 int ipp_kernel_time(ipp_t* h, int which, double* ms, int64_t* launches, int reset) {
     IPP_TRY
     E(h).kernelTime(which, ms, launches, reset != 0);

@@ -84,6 +84,28 @@ void launch_pack_rows(uint8_t* d_flags, int nSlots, int Tpad, const int* d_rowOf
 void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, int32_t* d_idsBvh, int32_t* d_idsBrute, float* d_t /*nullable: (tBvh, tBrute) per ray*/,
                          cudaStream_t st);
 int visibility_grid_blocks();
+
+// visibility_bins.cu -- the same sampling with depth-sorted leaf bins (meshes of <= kMaxBinLeaves leaves, images <= 1024 a side)
+constexpr int kMaxBinLeaves = 16384;
+struct BinBuffers {
+    unsigned long long* table = nullptr;      // [poses][stride] packed leaf entries, front to back
+    int* tableCount = nullptr;                // [poses] entries per pose
+    uint32_t* tileMask = nullptr;             // [poses][32] occupied 32x32 tiles, one word per tile row
+    unsigned long long* superMask = nullptr;  // [poses] occupied 128x128 supertiles (bit = sy * 8 + sx)
+    int* nSuper = nullptr;                    // [poses + 1] popcount of superMask
+    unsigned long long* scratch = nullptr;    // [gridBlocks * warps][stride] per-warp supertile lists
+    int stride = 0, gridBlocks = 0;
+};
+bool bins_supported(const DeviceScene& sc, const CameraParams& cam);
+int bins_grid_blocks();
+int bins_warps_per_block();
+int bins_table_stride(int nLeaves);
+void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, int nSnaps, const BinBuffers& b,
+                       cudaStream_t st);
+// d_superOffset = exclusive scan of BinBuffers::nSuper (nSnaps + 1 entries), totalSuper its last entry
+void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_superOffset, int nSnaps,
+                            int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters,
+                            cudaStream_t st);
 size_t scan_tmp_bytes(int n);
 void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);
 

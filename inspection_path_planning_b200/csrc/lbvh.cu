@@ -134,6 +134,38 @@ __global__ void k_emit(int n, const int* __restrict__ left, const int* __restric
     out[i] = nd;
 }
 
+// Leaf table: the leaf children of the live nodes (nodes inside a collapsed subtree are unreachable).
+__global__ void k_leaf_count(int n, const int* __restrict__ rlo, const int* __restrict__ rhi, const BvhNode* __restrict__ nodes,
+                             int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const bool live = i == 0 || rhi[i] - rlo[i] + 1 > kLeafMax;
+    int c = 0;
+    if (live) {
+        const int l0 = __float_as_int(nodes[i].q3.x), l1 = __float_as_int(nodes[i].q3.y);
+        c = (l0 < 0 && ((~l0) & kLeafMask) > 0) + (l1 < 0 && ((~l1) & kLeafMask) > 0);
+    }
+    counts[i] = c;
+}
+
+__global__ void k_leaf_fill(int n, const int* __restrict__ counts, const int* __restrict__ offsets, const BvhNode* __restrict__ nodes,
+                            float4* __restrict__ leafLo, float4* __restrict__ leafHi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1 || counts[i] == 0) return;
+    const BvhNode nd = nodes[i];
+    int o = offsets[i];
+    const int l0 = __float_as_int(nd.q3.x), l1 = __float_as_int(nd.q3.y);
+    if (l0 < 0 && ((~l0) & kLeafMask) > 0) {
+        leafLo[o] = make_float4(nd.q0.x, nd.q0.y, nd.q0.z, __int_as_float(~l0));
+        leafHi[o] = make_float4(nd.q0.w, nd.q1.x, nd.q1.y, 0.f);
+        o++;
+    }
+    if (l1 < 0 && ((~l1) & kLeafMask) > 0) {
+        leafLo[o] = make_float4(nd.q1.z, nd.q1.w, nd.q2.x, __int_as_float(~l1));
+        leafHi[o] = make_float4(nd.q2.y, nd.q2.z, nd.q2.w, 0.f);
+    }
+}
+
 __global__ void k_gather(const float* __restrict__ verts, const float* __restrict__ canon, const uint8_t* __restrict__ degenerate,
                          const int* __restrict__ vals, int n, float4* ta, float4* tb, float4* tc, float4* tn, float4* oa, float4* ob,
                          float4* oc) {
@@ -203,6 +235,21 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
         k_karras<<<G, B, 0, st>>>(keys2, n, left, right, rlo, rhi, parentI, parentL);
         k_refit<<<G, B, 0, st>>>(d_verts, vals2, n, left, right, parentI, parentL, leafMin, leafMax, nodeMin, nodeMax, arrive);
         k_emit<<<G, B, 0, st>>>(n, left, right, rlo, rhi, leafMin, leafMax, nodeMin, nodeMax, pad, sc.nodes);
+        // flat leaf table for the binned visibility kernel (arrive / parentI are free again: counts / offsets)
+        int *counts = arrive, *offsets = parentI;
+        k_leaf_count<<<G, B, 0, st>>>(n, rlo, rhi, sc.nodes, counts);
+        IPP_CUDA_CHECK(cudaMemsetAsync(counts + (n - 1), 0, sizeof(int), st));
+        size_t scanBytes = scan_tmp_bytes(n);
+        void* scanTmp = nullptr;
+        IPP_CUDA_CHECK(cudaMalloc(&scanTmp, scanBytes));
+        exclusive_scan_i32(counts, offsets, n, scanTmp, scanBytes, st);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(&sc.nLeaves, offsets + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        IPP_CUDA_CHECK(cudaStreamSynchronize(st));
+        sc.leafLo = dalloc<float4>(sc.nLeaves);
+        sc.leafHi = dalloc<float4>(sc.nLeaves);
+        k_leaf_fill<<<G, B, 0, st>>>(n, counts, offsets, sc.nodes, sc.leafLo, sc.leafHi);
+        IPP_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(scanTmp);
     } else {
         // single triangle: root with one leaf child and one empty child
         BvhNode nd;
@@ -215,6 +262,14 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
         memcpy(&f1, &l1, 4);
         nd.q3 = make_float4(f0, f1, 0.f, 0.f);
         IPP_CUDA_CHECK(cudaMemcpyAsync(sc.nodes, &nd, sizeof(nd), cudaMemcpyHostToDevice, st));
+        sc.nLeaves = 1;
+        sc.leafLo = dalloc<float4>(1);
+        sc.leafHi = dalloc<float4>(1);
+        float4 lo4 = make_float4(nd.q0.x, nd.q0.y, nd.q0.z, 0.f), hi4 = make_float4(nd.q0.w, nd.q1.x, nd.q1.y, 0.f);
+        int ref = (0 << kLeafShift) | 1;
+        memcpy(&lo4.w, &ref, 4);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(sc.leafLo, &lo4, sizeof(lo4), cudaMemcpyHostToDevice, st));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(sc.leafHi, &hi4, sizeof(hi4), cudaMemcpyHostToDevice, st));
     }
     IPP_CUDA_CHECK(cudaStreamSynchronize(st));
     IPP_CUDA_CHECK(cudaGetLastError());
@@ -236,6 +291,9 @@ void free_bvh(DeviceScene& sc) {
     cudaFree(sc.ta); cudaFree(sc.tb); cudaFree(sc.tc); cudaFree(sc.tn);
     cudaFree(sc.oa); cudaFree(sc.ob); cudaFree(sc.oc);
     cudaFree(sc.nodes);
+    cudaFree(sc.leafLo); cudaFree(sc.leafHi);
+    sc.leafLo = sc.leafHi = nullptr;
+    sc.nLeaves = 0;
     sc.ta = sc.tb = sc.tc = sc.tn = sc.oa = sc.ob = sc.oc = nullptr;
     sc.nodes = nullptr;
 }

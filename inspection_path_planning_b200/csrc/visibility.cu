@@ -19,21 +19,17 @@
 //  * Ng comes from an fp64 cross product (lbvh.cu), the fp32 one loses most digits on long thin triangles;
 //  * depth resolution: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins (GL_LESS on a
 //    fixed-point depth buffer, triangles drawn in id order).
-#include "kernels.h"
+#include "raster.cuh"
 
 namespace ipp {
 
 namespace {
 
+using namespace raster;
+
 constexpr int kVisWarps = 4;
 constexpr int kVisThreads = kVisWarps * 32;
 constexpr int kGrab = 4;        // tiles a warp claims per scheduling step
-constexpr int kTile = 32;       // tile side in pixels
-constexpr int kTilePixels = kTile * kTile;
-constexpr int kNoId = 0x7fffffff;
-constexpr float kDepthTie = 1.0f + 1.0f / 65536.0f;
-constexpr int kTriWords = 16;   // floats per staged triangle
-constexpr int kPending = 32;    // triangles staged together (one per lane)
 
 struct Hit {
     float t;
@@ -46,11 +42,6 @@ struct Hit {
 __device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) { return __fmaf_rn(a, b, -__fmul_rn(c, d)); }
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
-}
-
-__device__ __forceinline__ double ddiff(double a, double b, double c, double d) { return __fma_rn(a, b, -__dmul_rn(c, d)); }
-__device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
-    return __fma_rn(az, bz, __fma_rn(ay, by, __dmul_rn(ax, bx)));
 }
 
 // Edge normals with the eye at the origin.  e_a = D.Na, e_b = D.Nb, e_c = D.Nc are the homogeneous edge functions of a ray D.
@@ -123,76 +114,6 @@ struct WarpShared {
     Snapshot snap;                   // the camera pose of the current tile
 };
 
-// One lane sets up one leaf triangle for the current camera pose: 16 floats in shared memory --
-//   [0..2] [3..5] [6..8] edge functions e(X, Y) = o[0] + o[1] X + o[2] Y of the pixel ray D = f + X s + Y u, [9..11] the same for
-//   det = D.Ng, [12] vol = (A - eye).Ng, [13] triangle id, [15] nearest vertex depth (< 0: produces no fragment in this tile).
-// Everything is multiplied by sign(vol), so that a ray in front of the eye crosses the triangle iff all three edge functions are
-// >= 0 and det > 0.  Setup runs in fp64 from the exact fp32 vertices, the fp32 eye and the fp64 camera basis; only the final
-// coefficients are rounded to fp32 (in fp32 the normal of an edge that points at the camera, |A' x e| << |A'||e|, lost up to
-// 0.03 pixel).
-__device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
-                                               float oy, float oz, float zNear, float zcull, float tXmin, float tXmax, float tYmin,
-                                               float tYmax) {
-    const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
-    float valid = -1.f;
-    if (b.w == 0.f) {  // not degenerate
-        const double fX = sp->f[0], fY = sp->f[1], fZ = sp->f[2];
-        const double ax = (double)a.x - (double)ox, ay = (double)a.y - (double)oy, az = (double)a.z - (double)oz;
-        const double bx_ = (double)b.x - (double)ox, by_ = (double)b.y - (double)oy, bz_ = (double)b.z - (double)oz;
-        const double cx_ = (double)cc.x - (double)ox, cy_ = (double)cc.y - (double)oy, cz_ = (double)cc.z - (double)oz;
-        // camera-space depth of the vertices; the depth of a fragment is a convex combination of them
-        const float za = (float)ddot(ax, ay, az, fX, fY, fZ), zb = (float)ddot(bx_, by_, bz_, fX, fY, fZ),
-                    zc = (float)ddot(cx_, cy_, cz_, fX, fY, fZ);
-        const float zlo = fminf(za, fminf(zb, zc)), zhi = fmaxf(za, fmaxf(zb, zc));
-        if (zhi >= zNear * 0.9999f && zlo <= zcull * 1.000001f) {
-            const double sX = sp->s[0], sY = sp->s[1], sZ = sp->s[2];
-            const double uX = sp->u[0], uY = sp->u[1], uZ = sp->u[2];
-            const double ebcx = (double)cc.x - (double)b.x, ebcy = (double)cc.y - (double)b.y, ebcz = (double)cc.z - (double)b.z;
-            const double eacx = (double)cc.x - (double)a.x, eacy = (double)cc.y - (double)a.y, eacz = (double)cc.z - (double)a.z;
-            const double eabx = (double)b.x - (double)a.x, eaby = (double)b.y - (double)a.y, eabz = (double)b.z - (double)a.z;
-            // B' x (C-B);  C' x (A-C) = -(A' x (C-A));  A' x (B-A);  Ng = (B-A) x (C-A): every edge normal from the lower endpoint
-            const double nax = ddiff(by_, ebcz, bz_, ebcy), nay = ddiff(bz_, ebcx, bx_, ebcz), naz = ddiff(bx_, ebcy, by_, ebcx);
-            const double nbx = -ddiff(ay, eacz, az, eacy), nby = -ddiff(az, eacx, ax, eacz), nbz = -ddiff(ax, eacy, ay, eacx);
-            const double ncx = ddiff(ay, eabz, az, eaby), ncy = ddiff(az, eabx, ax, eabz), ncz = ddiff(ax, eaby, ay, eabx);
-            const double ngx = ddiff(eaby, eacz, eabz, eacy), ngy = ddiff(eabz, eacx, eabx, eacz), ngz = ddiff(eabx, eacy, eaby, eacx);
-            const double vol = ddot(ax, ay, az, ngx, ngy, ngz);  // (A - eye).Ng
-            const float sg = vol < 0.0 ? -1.f : 1.f;             // exact sign flip: shared edges stay bit-identical up to sign
-            valid = fmaxf(zlo, 0.f) * 0.999999f;
-            o[0] = sg * (float)ddot(nax, nay, naz, fX, fY, fZ); o[1] = sg * (float)ddot(nax, nay, naz, sX, sY, sZ); o[2] = sg * (float)ddot(nax, nay, naz, uX, uY, uZ);
-            o[3] = sg * (float)ddot(nbx, nby, nbz, fX, fY, fZ); o[4] = sg * (float)ddot(nbx, nby, nbz, sX, sY, sZ); o[5] = sg * (float)ddot(nbx, nby, nbz, uX, uY, uZ);
-            o[6] = sg * (float)ddot(ncx, ncy, ncz, fX, fY, fZ); o[7] = sg * (float)ddot(ncx, ncy, ncz, sX, sY, sZ); o[8] = sg * (float)ddot(ncx, ncy, ncz, uX, uY, uZ);
-            o[9] = sg * (float)ddot(ngx, ngy, ngz, fX, fY, fZ); o[10] = sg * (float)ddot(ngx, ngy, ngz, sX, sY, sZ); o[11] = sg * (float)ddot(ngx, ngy, ngz, uX, uY, uZ);
-            o[12] = sg * (float)vol;
-            o[13] = a.w;  // triangle id (int bits)
-            // can any pixel centre of the tile be inside?  Each edge function is monotone in X and in Y (also as computed), so its
-            // value at the extreme pixel centre of the tile bounds it over the tile.
-            const float ma = __fmaf_rn(o[1], o[1] >= 0.f ? tXmax : tXmin, __fmaf_rn(o[2], o[2] >= 0.f ? tYmax : tYmin, o[0]));
-            const float mb = __fmaf_rn(o[4], o[4] >= 0.f ? tXmax : tXmin, __fmaf_rn(o[5], o[5] >= 0.f ? tYmax : tYmin, o[3]));
-            const float mc = __fmaf_rn(o[7], o[7] >= 0.f ? tXmax : tXmin, __fmaf_rn(o[8], o[8] >= 0.f ? tYmax : tYmin, o[6]));
-            if (fminf(fminf(ma, mb), mc) < 0.f) valid = -1.f;
-        }
-    }
-    o[15] = valid;
-    return valid >= 0.f;
-}
-
-// last index s in [0, nSnaps) with tileOffset[s] <= task (tileOffset[0] == 0): 32-ary search, one probe per lane and round
-__device__ __forceinline__ int find_snapshot(const int* __restrict__ tileOffset, int nSnaps, long long task, int lane) {
-    int lo = 0, hi = nSnaps - 1;
-    while (hi > lo) {
-        int span = hi - lo;
-        int step = (span + 31) >> 5;
-        int pos = min(hi, lo + (lane + 1) * step);
-        bool le = (long long)__ldg(tileOffset + pos) <= task;
-        int k = __popc(__ballot_sync(0xffffffffu, le));
-        int nlo = k ? min(hi, lo + k * step) : lo;
-        int nhi = (k < 32) ? min(hi, lo + (k + 1) * step) - 1 : hi;
-        lo = nlo;
-        hi = max(nhi, nlo);
-    }
-    return lo;
-}
-
 __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
                                                             const int* __restrict__ tileOffset, int nSnaps, long long totalTiles,
                                                             uint8_t* __restrict__ flags, int32_t* __restrict__ idImage,
@@ -238,13 +159,7 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
             const int tpx0 = (rx0 + local % rnx) * kTile, tpy0 = (ry0 + local / rnx) * kTile;
             // ---- tile state ----
             const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
-#pragma unroll
-            for (int k = 0; k < kTilePixels / 32; ++k) {
-                // rays outside the image start with depth 0: no fragment can ever beat it
-                const bool inside = ((k & 3) * 8 + (lane & 7)) < vw && ((k >> 2) * 4 + (lane >> 3)) < vh;
-                S.t[k * 32 + lane] = inside ? zFar : 0.f;
-                S.id[k * 32 + lane] = kNoId;
-            }
+            tile_init(S.t, S.id, lane, vw, vh, zFar);
             float zcull = zFar * kDepthTie;  // nothing beyond this depth can matter to any ray of the tile
             // lane b keeps the depth beyond which nothing can matter to any ray of 8x4 block b (0: block outside the image)
             float bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zcull : 0.f;
@@ -260,15 +175,8 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                 case 4: nx = fx; ny = fy; nz = fz; thr = zNear * 0.9999f - 1e-4f; break;                 // zmax >= zNear
                 default: nx = -fx; ny = -fy; nz = -fz; thr = 0.f; break;                                 // zmin <= zcull (limit set per node)
             }
-            // image-plane position of this lane's pixel in block (0, 0); block (bx, by) adds (bx 8 kx, by 4 ky).  The same
-            // expression is used for a pixel whatever triangle is tested, so shared edges stay watertight.
-            const float Xl = __fmaf_rn((float)(tpx0 + (lane & 7)), kx, cx), Yl = __fmaf_rn((float)(tpy0 + (lane >> 3)), ky, cy);
-            const float kx8 = 8.f * kx, ky4 = 4.f * ky;
-            // extreme pixel centres of the tile and of block b = lane, by the same expressions the corner pixels use
-            const float tXmin = __fmaf_rn((float)tpx0, kx, cx), tXmax = __fmaf_rn(3.f, kx8, __fmaf_rn((float)(tpx0 + 7), kx, cx));
-            const float tYmin = __fmaf_rn((float)tpy0, ky, cy), tYmax = __fmaf_rn(7.f, ky4, __fmaf_rn((float)(tpy0 + 3), ky, cy));
-            const float bXmin = __fmaf_rn((float)(lane & 3), kx8, __fmaf_rn((float)tpx0, kx, cx)), bXmax = __fmaf_rn((float)(lane & 3), kx8, __fmaf_rn((float)(tpx0 + 7), kx, cx));
-            const float bYmin = __fmaf_rn((float)(lane >> 2), ky4, __fmaf_rn((float)tpy0, ky, cy)), bYmax = __fmaf_rn((float)(lane >> 2), ky4, __fmaf_rn((float)(tpy0 + 3), ky, cy));
+            TileGeom tg;
+            tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
             __syncwarp();
 
             // ---- frustum-packet traversal ----
@@ -285,57 +193,15 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                     // ---- flush the pending triangles ----
                     __syncwarp();
                     bool mine = false;
-                    if (lane < pend) mine = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tXmin, tXmax, tYmin, tYmax);
-                    unsigned live = __ballot_sync(0xffffffffu, mine);  // triangles that can produce a fragment in this tile
-                    bool dirty = false;
-                    while (live) {
-                        const int k = __ffs(live) - 1;
-                        live &= live - 1;
-                        const float* tr = S.tri[k];
-                        const float zloTri = tr[15];
-                        if (zloTri > zcull) continue;
-                        const float eaf = tr[0], eas = tr[1], eau = tr[2], ebf = tr[3], ebs = tr[4], ebu = tr[5], ecf = tr[6], ecs = tr[7],
-                                    ecu = tr[8], gf = tr[9], gs = tr[10], gu = tr[11], vol = tr[12];
-                        const int id = __float_as_int(tr[13]);
-                        // which 8x4 blocks can hold a fragment that matters: lane b answers for block b.  An edge function is
-                        // monotone in X and in Y, also as computed, so its value at the extreme pixel centre bounds the block.
-                        const float ca = __fmaf_rn(eas, eas >= 0.f ? bXmax : bXmin, __fmaf_rn(eau, eau >= 0.f ? bYmax : bYmin, eaf));
-                        const float cb = __fmaf_rn(ebs, ebs >= 0.f ? bXmax : bXmin, __fmaf_rn(ebu, ebu >= 0.f ? bYmax : bYmin, ebf));
-                        const float cc = __fmaf_rn(ecs, ecs >= 0.f ? bXmax : bXmin, __fmaf_rn(ecu, ecu >= 0.f ? bYmax : bYmin, ecf));
-                        unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && zloTri <= bzReg);
-                        while (todo) {
-                            const int blk = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const float X = __fmaf_rn((float)(blk & 3), kx8, Xl), Y = __fmaf_rn((float)(blk >> 2), ky4, Yl);
-                            const float eu = __fmaf_rn(eas, X, __fmaf_rn(eau, Y, eaf)), ev = __fmaf_rn(ebs, X, __fmaf_rn(ebu, Y, ebf)),
-                                        ew = __fmaf_rn(ecs, X, __fmaf_rn(ecu, Y, ecf));
-                            if (fminf(fminf(eu, ev), ew) >= 0.f) {  // the ray crosses the triangle
-                                const float det = gs * X + (gu * Y + gf);
-                                const float t = __fdividef(vol, det);  // det == 0: inf / NaN fails the range test
-                                const int idx = blk * 32 + lane;
-                                const float ht = S.t[idx];
-                                if (t >= zNear && t <= zFar && t <= ht * kDepthTie) {
-                                    const int hid = S.id[idx];
-                                    S.id[idx] = (t * kDepthTie < ht) ? id : min(hid, id);
-                                    S.t[idx] = fminf(ht, t);
-                                    dirty = true;
-                                }
-                            }
-                        }
-                    }
+                    if (lane < pend) mine = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
+                    const unsigned live = __ballot_sync(0xffffffffu, mine);  // triangles that can produce a fragment in this tile
+                    __syncwarp();
+                    const bool dirty = raster_staged(live, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
                     pend = 0;
                     if (__any_sync(0xffffffffu, dirty)) {
                         tileHit = true;
-                        // hierarchical depth culling: lane b takes the farthest hit of block b (conflict-free diagonal walk);
-                        // rays without a hit still hold zFar, rays outside the image hold 0
                         __syncwarp();
-                        float zm = 0.f;
-#pragma unroll 8
-                        for (int j = 0; j < 32; ++j) zm = fmaxf(zm, S.t[lane * 32 + ((j + lane) & 31)]);
-                        zm *= kDepthTie;
-                        bzReg = zm;
-                        for (int o2 = 16; o2; o2 >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o2));
-                        zcull = zm;
+                        refresh_depth_bounds(S.t, lane, bzReg, zcull);
                     }
                 }
                 if (!more) break;
@@ -395,19 +261,8 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
                 }
             }
             __syncwarp();
-            // ---- the winners: one byte store per run of equal ids inside an 8x4 block ----
-            if (tileHit || idImage)
-#pragma unroll 4
-            for (int k = 0; k < kTilePixels / 32; ++k) {
-                const int id = S.id[k * 32 + lane];
-                const int left = __shfl_up_sync(0xffffffffu, id, 1), up = __shfl_up_sync(0xffffffffu, id, 8);
-                const bool dupe = ((lane & 7) != 0 && left == id) || (lane >= 8 && up == id);
-                if (id != kNoId && !dupe) flags[(size_t)S.snap.slot * sc.Tpad + id] = 1;
-                if (idImage) {
-                    const int px = tpx0 + (k & 3) * 8 + (lane & 7), py = tpy0 + (k >> 2) * 4 + (lane >> 3);
-                    if (px < cam.W && py < cam.H) idImage[(size_t)py * cam.W + px] = id == kNoId ? -1 : id;
-                }
-            }
+            // ---- the winners ----
+            if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
             if (lane == 0) myRays += (unsigned long long)(vw * vh);
             myTiles++;
             __syncwarp();

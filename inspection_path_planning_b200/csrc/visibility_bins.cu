@@ -1,0 +1,390 @@
+// visibility_bins.cu -- K4b: edge visibility with depth-sorted leaf bins instead of a BVH walk per tile.  Same item-buffer sampling
+// and the same per-tile rasteriser as visibility.cu (raster.cuh); what changes is how a tile finds its triangles.
+//
+//   k_leaf_table  one CTA per camera pose: every BVH leaf box (a few thousand for the reference's meshes) is projected -- 8 corners,
+//                 screen rectangle in 32x32-pixel tile units with a one-pixel margin, nearest depth -- culled against the view
+//                 volume, packed into one 64-bit word [depth:16 | tx0 tx1 ty0 ty1:20 | first triangle, count:28] and block-radix
+//                 sorted by depth (cub::BlockRadixSort, stable, so the order is deterministic).  The CTA also ORs the rectangles
+//                 into a 32x32 tile occupancy mask and an 8x8 supertile mask: empty tiles are never scheduled.
+//   k_visibility_bins  persistent grid, one warp per occupied 128x128 supertile: one coalesced pass over the pose's table keeps the
+//                 entries that touch the supertile (per-warp list in an L2-resident scratch), then the warp rasterises its <= 16
+//                 tiles one after the other.  A tile walks the list front to back, queues the triangles of the leaves whose
+//                 rectangle contains it, and stops at the first entry behind its farthest hit -- strict front-to-back order makes
+//                 the hierarchical depth culling of raster.cuh bite much earlier than the approximate order of a BVH walk, and
+//                 there is no dependent node fetch left on the critical path.
+//
+// Used when the mesh has <= kMaxLeaves leaves and the image is <= 1024 pixels a side (every asset of the reference); larger
+// inputs take the BVH-walking kernel of visibility.cu.
+#include <cub/block/block_radix_sort.cuh>
+
+#include "raster.cuh"
+
+namespace ipp {
+
+namespace {
+
+using namespace raster;
+
+constexpr int kBinWarps = 4;
+constexpr int kBinThreads = kBinWarps * 32;
+constexpr unsigned long long kNoEntry = ~0ull;
+
+struct BinShared {
+    float t[kTilePixels];
+    int id[kTilePixels];
+    float tri[kPending][kTriWords];
+    Snapshot snap;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// leaf table
+// ---------------------------------------------------------------------------------------------------------------------
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_leaf_table(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps, int stride,
+                                                        unsigned long long* __restrict__ table, int* __restrict__ tableCount,
+                                                        uint32_t* __restrict__ tileMask, unsigned long long* __restrict__ superMask,
+                                                        int* __restrict__ nSuper) {
+    using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS>;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(smemRaw);
+    __shared__ unsigned rowMask[32];
+    __shared__ int nValid;
+    __shared__ unsigned superHalf[2];
+
+    const int si = blockIdx.x, tid = threadIdx.x;
+    const Snapshot& sp = snaps[si];
+    if (sp.rnx == 0 || sp.rny == 0) {  // the scene box is outside the view volume (make_snapshot)
+        if (tid < 32) tileMask[(size_t)si * 32 + tid] = 0u;
+        if (tid == 0) { tableCount[si] = 0; superMask[si] = 0ull; nSuper[si] = 0; }
+        return;
+    }
+    if (tid < 32) rowMask[tid] = 0u;
+    if (tid == 0) nValid = 0;
+    __syncthreads();
+
+    const float ox = sp.eye[0], oy = sp.eye[1], oz = sp.eye[2];
+    const float fx = (float)sp.f[0], fy = (float)sp.f[1], fz = (float)sp.f[2];
+    const float sx = (float)sp.s[0], sy = (float)sp.s[1], sz = (float)sp.s[2];
+    const float ux = (float)sp.u[0], uy = (float)sp.u[1], uz = (float)sp.u[2];
+    const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
+    const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
+    const float ikx = 1.f / kx, iky = 1.f / ky;
+    const float zFarCull = cam.zFar * kDepthTie;
+    const float qscale = 65535.f / (zFarCull * 1.000001f + 1e-4f);
+    // fragments exist only at depth >= zNear: boxes are clipped at a plane just inside it before they are projected (a near plane
+    // closer than 1 cm leaves no headroom for the fp32 projection: such boxes take the whole image when they straddle it)
+    const float zClip = cam.zNear * 0.999f, izClip = 1.f / zClip;
+    const bool clipOk = zClip >= 0.01f;
+    const int txMax = (cam.W - 1) >> 5, tyMax = (cam.H - 1) >> 5;
+
+    unsigned long long keys[ITEMS];
+    int mine = 0;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int leaf = it * THREADS + tid;
+        keys[it] = kNoEntry;
+        if (leaf >= sc.nLeaves) continue;
+        const float4 lo4 = __ldg(sc.leafLo + leaf), hi4 = __ldg(sc.leafHi + leaf);
+        const float lx = lo4.x - ox, ly = lo4.y - oy, lz = lo4.z - oz, hx = hi4.x - ox, hy = hi4.y - oy, hz = hi4.z - oz;
+        // camera-space coordinates of the corners are sums of one term per axis
+        const float zx0 = fx * lx, zx1 = fx * hx, zy0 = fy * ly, zy1 = fy * hy, zz0 = fz * lz, zz1 = fz * hz;
+        const float zmin = fminf(zx0, zx1) + fminf(zy0, zy1) + fminf(zz0, zz1);
+        const float zmax = fmaxf(zx0, zx1) + fmaxf(zy0, zy1) + fmaxf(zz0, zz1);
+        if (zmax < cam.zNear * 0.9999f - 1e-4f || zmin > zFarCull * 1.000001f + 1e-4f) continue;
+        int px0 = 0, px1 = cam.W - 1, py0 = 0, py1 = cam.H - 1;
+        if (zmin >= zClip || clipOk) {
+            // screen rectangle of the part of the box in front of the plane z = zClip (just inside the near plane): its corners in
+            // front of the plane and the points where its edges cross the plane
+            const float xx0 = sx * lx, xx1 = sx * hx, xy0 = sy * ly, xy1 = sy * hy, xz0 = sz * lz, xz1 = sz * hz;
+            const float yx0 = ux * lx, yx1 = ux * hx, yy0 = uy * ly, yy1 = uy * hy, yz0 = uz * lz, yz1 = uz * hz;
+            float Xmin = 1e30f, Xmax = -1e30f, Ymin = 1e30f, Ymax = -1e30f;
+            float cxs[8], cys[8], czs[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                czs[c] = ((c & 1) ? zx1 : zx0) + ((c & 2) ? zy1 : zy0) + ((c & 4) ? zz1 : zz0);
+                cxs[c] = ((c & 1) ? xx1 : xx0) + ((c & 2) ? xy1 : xy0) + ((c & 4) ? xz1 : xz0);
+                cys[c] = ((c & 1) ? yx1 : yx0) + ((c & 2) ? yy1 : yy0) + ((c & 4) ? yz1 : yz0);
+                if (czs[c] >= zClip) {
+                    const float iz = 1.f / czs[c];
+                    const float X = cxs[c] * iz, Y = cys[c] * iz;
+                    Xmin = fminf(Xmin, X); Xmax = fmaxf(Xmax, X);
+                    Ymin = fminf(Ymin, Y); Ymax = fmaxf(Ymax, Y);
+                }
+            }
+            if (zmin < zClip) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                    for (int ax = 1; ax <= 4; ax <<= 1) {
+                        if (c & ax) continue;  // every edge once, from its lower corner
+                        const int d = c | ax;
+                        if ((czs[c] >= zClip) != (czs[d] >= zClip)) {
+                            const float t = (zClip - czs[c]) / (czs[d] - czs[c]);
+                            const float X = (cxs[c] + t * (cxs[d] - cxs[c])) * izClip, Y = (cys[c] + t * (cys[d] - cys[c])) * izClip;
+                            Xmin = fminf(Xmin, X); Xmax = fmaxf(Xmax, X);
+                            Ymin = fminf(Ymin, Y); Ymax = fmaxf(Ymax, Y);
+                        }
+                    }
+                }
+            }
+            // pixel centres X(px) = px kx + cx inside [Xmin, Xmax], widened by one pixel against rounding
+            const float a0 = fminf(fmaxf((Xmin - cx) * ikx, -1e6f), 1e6f), a1 = fminf(fmaxf((Xmax - cx) * ikx, -1e6f), 1e6f);
+            const float b0 = fminf(fmaxf((Ymin - cy) * iky, -1e6f), 1e6f), b1 = fminf(fmaxf((Ymax - cy) * iky, -1e6f), 1e6f);
+            px0 = (int)floorf(a0) - 1; px1 = (int)ceilf(a1) + 1;
+            py0 = (int)floorf(b0) - 1; py1 = (int)ceilf(b1) + 1;
+            if (px1 < 0 || py1 < 0 || px0 > cam.W - 1 || py0 > cam.H - 1) continue;
+            px0 = max(px0, 0); py0 = max(py0, 0);
+            px1 = min(px1, cam.W - 1); py1 = min(py1, cam.H - 1);
+        }
+        const unsigned tx0 = px0 >> 5, tx1 = min(px1 >> 5, txMax), ty0 = py0 >> 5, ty1 = min(py1 >> 5, tyMax);
+        const unsigned zq = (unsigned)fminf(65534.f, floorf(fmaxf(zmin, 0.f) * qscale));
+        const unsigned ref = (unsigned)__float_as_int(lo4.w) & 0x0fffffffu;
+        keys[it] = ((unsigned long long)zq << 48) | ((unsigned long long)tx0 << 43) | ((unsigned long long)tx1 << 38) |
+                   ((unsigned long long)ty0 << 33) | ((unsigned long long)ty1 << 28) | ref;
+        const unsigned bits = ((2u << tx1) - 1u) & ~((1u << tx0) - 1u);
+        for (unsigned ty = ty0; ty <= ty1; ++ty) atomicOr(&rowMask[ty], bits);
+        mine++;
+    }
+    if (mine) atomicAdd(&nValid, mine);
+    Sort(temp).Sort(keys, 48, 64);  // stable: entries of equal depth keep their (fixed) input order
+    __syncthreads();
+    unsigned long long* out = table + (size_t)si * stride;
+    const int n = nValid;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int pos = tid * ITEMS + it;
+        if (pos < n) out[pos] = keys[it];
+    }
+    if (tid < 64) {
+        const int ssx = tid & 7, ssy = tid >> 3;
+        const unsigned any = (rowMask[4 * ssy] | rowMask[4 * ssy + 1] | rowMask[4 * ssy + 2] | rowMask[4 * ssy + 3]) & (0xFu << (4 * ssx));
+        const unsigned b = __ballot_sync(0xffffffffu, any != 0u);
+        if ((tid & 31) == 0) superHalf[tid >> 5] = b;
+    }
+    if (tid < 32) tileMask[(size_t)si * 32 + tid] = rowMask[tid];
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long m = (unsigned long long)superHalf[0] | ((unsigned long long)superHalf[1] << 32);
+        tableCount[si] = n;
+        superMask[si] = m;
+        nSuper[si] = __popcll(m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4b
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
+                                                                 const int* __restrict__ superOffset, int nSnaps,
+                                                                 const unsigned long long* __restrict__ table, int stride,
+                                                                 const int* __restrict__ tableCount, const uint32_t* __restrict__ tileMask,
+                                                                 const unsigned long long* __restrict__ superMask,
+                                                                 unsigned long long* scratch, uint8_t* __restrict__ flags,
+                                                                 int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters) {
+    __shared__ BinShared s_all[kBinWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BinShared& S = s_all[warp];
+    unsigned long long* list = scratch + (size_t)(blockIdx.x * kBinWarps + warp) * stride;
+    unsigned long long myRays = 0, myEntries = 0;
+    unsigned myTris = 0, myTiles = 0;  // statistics (lane 0 only matters)
+    const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
+    const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
+    const float zNear = cam.zNear, zFar = cam.zFar;
+    const float iq = (zFar * kDepthTie * 1.000001f + 1e-4f) / 65535.f;  // depth of a quantised table entry (a lower bound)
+    const long long totalSuper = (long long)__ldg(superOffset + nSnaps);
+    const unsigned ltMask = (1u << lane) - 1u;
+
+    while (true) {
+        long long task = 0;
+        if (lane == 0) task = (long long)atomicAdd(&counters[1], 1ull);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= totalSuper) break;
+        const int si = find_snapshot(superOffset, nSnaps, task, lane);
+        __syncwarp();
+        {
+            const int* src = (const int*)(snaps + si);
+            int* dst = (int*)&S.snap;
+            if (lane < (int)(sizeof(Snapshot) / 4)) dst[lane] = __ldg(src + lane);
+        }
+        __syncwarp();
+        const float ox = S.snap.eye[0], oy = S.snap.eye[1], oz = S.snap.eye[2];
+        // the k-th occupied supertile of this pose
+        int sbit;
+        {
+            unsigned long long m = __ldg(superMask + si);
+            for (int k = (int)(task - (long long)__ldg(superOffset + si)); k > 0; --k) m &= m - 1;
+            sbit = __ffsll((long long)m) - 1;
+        }
+        const unsigned ssx = sbit & 7, ssy = sbit >> 3;
+
+        // ---- phase 1: the table entries that touch this supertile, still front to back ----
+        const int nEnt = __ldg(tableCount + si);
+        const unsigned long long* tab = table + (size_t)si * stride;
+        int L = 0;
+        for (int base = 0; base < nEnt; base += 32) {
+            const int i = base + lane;
+            const unsigned long long e = i < nEnt ? __ldg(tab + i) : 0ull;
+            const unsigned r = (unsigned)(e >> 28);
+            const unsigned tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
+            const bool ok = i < nEnt && (tx0 >> 2) <= ssx && (tx1 >> 2) >= ssx && (ty0 >> 2) <= ssy && (ty1 >> 2) >= ssy;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) list[L + __popc(m & ltMask)] = e;
+            L += __popc(m);
+        }
+        myEntries += (unsigned long long)nEnt;
+        __syncwarp();
+
+        // ---- phase 2: the occupied tiles of the supertile ----
+        for (int tl = 0; tl < 16; ++tl) {
+            const int tx = (int)ssx * 4 + (tl & 3), ty = (int)ssy * 4 + (tl >> 2);
+            const int tpx0 = tx * kTile, tpy0 = ty * kTile;
+            if (tpx0 >= cam.W || tpy0 >= cam.H) continue;
+            const bool occupied = (__ldg(tileMask + (size_t)si * 32 + ty) >> tx) & 1u;
+            if (!occupied && !idImage) continue;
+            const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
+            float zcull = zFar * kDepthTie;  // nothing beyond this depth can matter to any ray of the tile
+            // lane b keeps the depth beyond which nothing can matter to any ray of 8x4 block b (0: block outside the image)
+            float bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zcull : 0.f;
+            TileGeom tg;
+            tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
+            bool inited = false, tileHit = false, done = !occupied || L == 0;
+            int pend = 0, myTri = 0, base = 0;
+            unsigned m = 0;
+            unsigned long long e = 0ull;
+            float zl = 0.f;
+            for (;;) {
+                // ---- next leaf whose rectangle contains the tile ----
+                bool have = false;
+                int first = 0, cnt = 0;
+                while (!done && !have) {
+                    const float bound = zcull * 1.000001f + 1e-4f;
+                    if (m == 0u) {
+                        if (base >= L) { done = true; break; }
+                        const int i = base + lane;
+                        e = i < L ? list[i] : kNoEntry;
+                        zl = (float)(unsigned)(e >> 48) * iq;
+                        // sorted by depth: when the first entry of the chunk is behind the farthest hit, so is everything after it
+                        if (__shfl_sync(0xffffffffu, zl, 0) > bound) { done = true; break; }
+                        const unsigned r = (unsigned)(e >> 28);
+                        const int tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
+                        m = __ballot_sync(0xffffffffu, i < L && tx0 <= tx && tx <= tx1 && ty0 <= ty && ty <= ty1 && zl <= bound);
+                        base += 32;
+                        myEntries += 32ull;
+                        continue;
+                    }
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (__shfl_sync(0xffffffffu, zl, k) > bound) { m = 0u; continue; }  // later entries of the chunk are farther still
+                    const unsigned ref = __shfl_sync(0xffffffffu, (unsigned)e, k) & 0x0fffffffu;
+                    first = (int)(ref >> kLeafShift);
+                    cnt = (int)(ref & kLeafMask);
+                    have = true;
+                }
+                if ((have && pend + cnt > kPending) || (done && pend > 0)) {
+                    // ---- flush: set the pending triangles up in parallel, one per lane, then test them one after the other ----
+                    __syncwarp();
+                    bool mineOk = false;
+                    if (lane < pend) mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
+                    const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
+                    myTris += pend;
+                    pend = 0;
+                    if (live) {
+                        if (!inited) {
+                            tile_init(S.t, S.id, lane, vw, vh, zFar);
+                            inited = true;
+                        }
+                        __syncwarp();
+                        const bool dirty = raster_staged(live, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
+                        if (__any_sync(0xffffffffu, dirty)) {
+                            tileHit = true;
+                            __syncwarp();
+                            refresh_depth_bounds(S.t, lane, bzReg, zcull);
+                        }
+                    }
+                }
+                if (have) {
+                    if (lane >= pend && lane < pend + cnt) myTri = first + lane - pend;
+                    pend += cnt;
+                } else if (done) {
+                    break;
+                }
+            }
+            __syncwarp();
+            // ---- the winners ----
+            if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
+            __syncwarp();
+            if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
+            myRays += (unsigned long long)(vw * vh);
+            myTiles++;
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && myTiles) {
+        atomicAdd(&counters[0], myRays);
+        atomicAdd(&counters[3], (unsigned long long)myTris);
+        atomicAdd(&counters[4], (unsigned long long)myTiles);
+        atomicAdd(&counters[5], myEntries);
+    }
+}
+
+template <int THREADS, int ITEMS>
+void launch_leaf_table_t(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, int nSnaps, const BinBuffers& b,
+                         cudaStream_t st) {
+    using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS>;
+    const size_t smem = sizeof(typename Sort::TempStorage);
+    static bool configured = false;
+    if (!configured) {
+        IPP_CUDA_CHECK(cudaFuncSetAttribute(k_leaf_table<THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    k_leaf_table<THREADS, ITEMS><<<nSnaps, THREADS, smem, st>>>(sc, cam, d_snaps, b.stride, b.table, b.tableCount, b.tileMask, b.superMask,
+                                                               b.nSuper);
+}
+
+}  // namespace
+
+bool bins_supported(const DeviceScene& sc, const CameraParams& cam) {
+    return sc.nLeaves > 0 && sc.nLeaves <= kMaxBinLeaves && cam.W <= 1024 && cam.H <= 1024 && sc.T < (1 << 24);
+}
+
+int bins_grid_blocks() {
+    int dev = 0, sms = 148, perSM = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_visibility_bins, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_visibility_bins, kBinThreads, 0);
+    if (perSM < 1) perSM = 1;
+    return sms * perSM;
+}
+int bins_warps_per_block() { return kBinWarps; }
+
+// stride of a pose's table: the leaf count rounded up to what the sort tile of its size class holds
+int bins_table_stride(int nLeaves) {
+    if (nLeaves <= 1024) return 1024;
+    if (nLeaves <= 4096) return 4096;
+    if (nLeaves <= 8192) return 8192;
+    return kMaxBinLeaves;
+}
+
+void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, int nSnaps, const BinBuffers& b,
+                       cudaStream_t st) {
+    if (nSnaps <= 0) return;
+    if (sc.nLeaves <= 1024) launch_leaf_table_t<256, 4>(sc, cam, d_snaps, nSnaps, b, st);
+    else if (sc.nLeaves <= 4096) launch_leaf_table_t<256, 16>(sc, cam, d_snaps, nSnaps, b, st);
+    else if (sc.nLeaves <= 8192) launch_leaf_table_t<512, 16>(sc, cam, d_snaps, nSnaps, b, st);
+    else launch_leaf_table_t<1024, 16>(sc, cam, d_snaps, nSnaps, b, st);
+}
+
+void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_superOffset, int nSnaps,
+                            int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters,
+                            cudaStream_t st) {
+    if (totalSuper <= 0 || nSnaps <= 0) return;
+    long long groups = (totalSuper + kBinWarps - 1) / kBinWarps;
+    int grid = (int)std::min<long long>(b.gridBlocks, groups);
+    // counters[1] is the work cursor of this launch
+    cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
+    k_visibility_bins<<<grid, kBinThreads, 0, st>>>(sc, cam, d_snaps, d_superOffset, nSnaps, b.table, b.stride, b.tableCount, b.tileMask,
+                                                   b.superMask, b.scratch, d_flags, d_idImage, d_counters);
+}
+
+}  // namespace ipp
