@@ -140,24 +140,37 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
         const float cb = __fmaf_rn(ebs, ebs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(ebu, ebu >= 0.f ? g.bYmax : g.bYmin, ebf));
         const float cc = __fmaf_rn(ecs, ecs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(ecu, ecu >= 0.f ? g.bYmax : g.bYmin, ecf));
         unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && zloTri <= bz);
+        // two blocks per step: their tests are independent (different pixels), which hides the latency of one behind the other
         while (todo) {
-            const int blk = __ffs(todo) - 1;
+            const int blk0 = __ffs(todo) - 1;
             todo &= todo - 1;
-            const float X = __fmaf_rn((float)(blk & 3), g.kx8, g.Xl), Y = __fmaf_rn((float)(blk >> 2), g.ky4, g.Yl);
-            const float eu = __fmaf_rn(eas, X, __fmaf_rn(eau, Y, eaf)), ev = __fmaf_rn(ebs, X, __fmaf_rn(ebu, Y, ebf)),
-                        ew = __fmaf_rn(ecs, X, __fmaf_rn(ecu, Y, ecf));
-            if (fminf(fminf(eu, ev), ew) >= 0.f) {  // the ray crosses the triangle
-                const float det = gs * X + (gu * Y + gf);
-                const float t = __fdividef(vol, det);  // det == 0: inf / NaN fails the range test
-                const int idx = blk * 32 + lane;
-                const float ht = St[idx];
-                // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
-                if (t >= zNear && t <= zFar && t <= ht * kDepthTie) {
-                    const int hid = Sid[idx];
-                    Sid[idx] = (t * kDepthTie < ht) ? id : min(hid, id);  // clearly nearer: replace; inside the band: lowest id
-                    St[idx] = fminf(ht, t);
-                    dirty = true;
-                }
+            const bool two = todo != 0u;
+            const int blk1 = two ? __ffs(todo) - 1 : blk0;
+            todo &= todo - 1;  // no-op on 0
+            const float X0 = __fmaf_rn((float)(blk0 & 3), g.kx8, g.Xl), Y0 = __fmaf_rn((float)(blk0 >> 2), g.ky4, g.Yl);
+            const float X1 = __fmaf_rn((float)(blk1 & 3), g.kx8, g.Xl), Y1 = __fmaf_rn((float)(blk1 >> 2), g.ky4, g.Yl);
+            const float eu0 = __fmaf_rn(eas, X0, __fmaf_rn(eau, Y0, eaf)), ev0 = __fmaf_rn(ebs, X0, __fmaf_rn(ebu, Y0, ebf)),
+                        ew0 = __fmaf_rn(ecs, X0, __fmaf_rn(ecu, Y0, ecf));
+            const float eu1 = __fmaf_rn(eas, X1, __fmaf_rn(eau, Y1, eaf)), ev1 = __fmaf_rn(ebs, X1, __fmaf_rn(ebu, Y1, ebf)),
+                        ew1 = __fmaf_rn(ecs, X1, __fmaf_rn(ecu, Y1, ecf));
+            const bool in0 = fminf(fminf(eu0, ev0), ew0) >= 0.f;         // the ray crosses the triangle
+            const bool in1 = two && fminf(fminf(eu1, ev1), ew1) >= 0.f;
+            const float t0 = __fdividef(vol, gs * X0 + (gu * Y0 + gf));  // det == 0: inf / NaN fails the range test
+            const float t1 = __fdividef(vol, gs * X1 + (gu * Y1 + gf));
+            const int idx0 = blk0 * 32 + lane, idx1 = blk1 * 32 + lane;
+            const float ht0 = St[idx0], ht1 = St[idx1];
+            // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
+            if (in0 && t0 >= zNear && t0 <= zFar && t0 <= ht0 * kDepthTie) {
+                const int hid = Sid[idx0];
+                Sid[idx0] = (t0 * kDepthTie < ht0) ? id : min(hid, id);  // clearly nearer: replace; inside the band: lowest id
+                St[idx0] = fminf(ht0, t0);
+                dirty = true;
+            }
+            if (in1 && t1 >= zNear && t1 <= zFar && t1 <= ht1 * kDepthTie) {
+                const int hid = Sid[idx1];
+                Sid[idx1] = (t1 * kDepthTie < ht1) ? id : min(hid, id);
+                St[idx1] = fminf(ht1, t1);
+                dirty = true;
             }
         }
     }

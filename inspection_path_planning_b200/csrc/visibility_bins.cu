@@ -28,13 +28,16 @@ using namespace raster;
 constexpr int kBinWarps = 4;
 constexpr int kBinThreads = kBinWarps * 32;
 constexpr unsigned long long kNoEntry = ~0ull;
+constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
 
 struct BinShared {
     float t[kTilePixels];
     int id[kTilePixels];
     float tri[kPending][kTriWords];
+    uint8_t queue[32 * kLeafMax];  // triangles of one list chunk waiting for set-up: (source lane << 3) | triangle of its leaf
     Snapshot snap;
 };
+static_assert(kLeafMax <= 8, "queue entries hold 3 bits of triangle index");
 
 // ---------------------------------------------------------------------------------------------------------------------
 // leaf table
@@ -44,9 +47,10 @@ __global__ void __launch_bounds__(THREADS) k_leaf_table(DeviceScene sc, CameraPa
                                                         unsigned long long* __restrict__ table, int* __restrict__ tableCount,
                                                         uint32_t* __restrict__ tileMask, unsigned long long* __restrict__ superMask,
                                                         int* __restrict__ nSuper) {
-    using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS>;
+    using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS, cub::NullType, kSortRadixBits>;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(smemRaw);
+    unsigned long long* stage = reinterpret_cast<unsigned long long*>(smemRaw);  // keys before the sort (same bytes as temp)
     __shared__ unsigned rowMask[32];
     __shared__ int nValid;
     __shared__ unsigned superHalf[2];
@@ -77,12 +81,11 @@ __global__ void __launch_bounds__(THREADS) k_leaf_table(DeviceScene sc, CameraPa
     const bool clipOk = zClip >= 0.01f;
     const int txMax = (cam.W - 1) >> 5, tyMax = (cam.H - 1) >> 5;
 
-    unsigned long long keys[ITEMS];
     int mine = 0;
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int leaf = it * THREADS + tid;
-        keys[it] = kNoEntry;
+    // one leaf per thread and step, not unrolled: the body is long and ITEMS copies of it would not fit the instruction cache
+#pragma unroll 1
+    for (int leaf = tid; leaf < THREADS * ITEMS; leaf += THREADS) {
+        stage[leaf] = kNoEntry;
         if (leaf >= sc.nLeaves) continue;
         const float4 lo4 = __ldg(sc.leafLo + leaf), hi4 = __ldg(sc.leafHi + leaf);
         const float lx = lo4.x - ox, ly = lo4.y - oy, lz = lo4.z - oz, hx = hi4.x - ox, hy = hi4.y - oy, hz = hi4.z - oz;
@@ -137,16 +140,22 @@ __global__ void __launch_bounds__(THREADS) k_leaf_table(DeviceScene sc, CameraPa
             px1 = min(px1, cam.W - 1); py1 = min(py1, cam.H - 1);
         }
         const unsigned tx0 = px0 >> 5, tx1 = min(px1 >> 5, txMax), ty0 = py0 >> 5, ty1 = min(py1 >> 5, tyMax);
-        const unsigned zq = (unsigned)fminf(65534.f, floorf(fmaxf(zmin, 0.f) * qscale));
+        // depth in 2^-12 steps of the culling range (the low 4 of the 16 key bits stay 0: fewer sort passes)
+        const unsigned zq = (unsigned)fminf(65534.f, floorf(fmaxf(zmin, 0.f) * qscale)) & 0xfff0u;
         const unsigned ref = (unsigned)__float_as_int(lo4.w) & 0x0fffffffu;
-        keys[it] = ((unsigned long long)zq << 48) | ((unsigned long long)tx0 << 43) | ((unsigned long long)tx1 << 38) |
+        stage[leaf] = ((unsigned long long)zq << 48) | ((unsigned long long)tx0 << 43) | ((unsigned long long)tx1 << 38) |
                    ((unsigned long long)ty0 << 33) | ((unsigned long long)ty1 << 28) | ref;
         const unsigned bits = ((2u << tx1) - 1u) & ~((1u << tx0) - 1u);
         for (unsigned ty = ty0; ty <= ty1; ++ty) atomicOr(&rowMask[ty], bits);
         mine++;
     }
     if (mine) atomicAdd(&nValid, mine);
-    Sort(temp).Sort(keys, 48, 64);  // stable: entries of equal depth keep their (fixed) input order
+    __syncthreads();
+    unsigned long long keys[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) keys[it] = stage[it * THREADS + tid];
+    __syncthreads();
+    Sort(temp).Sort(keys, 52, 64);  // stable: entries of equal depth keep their (fixed) input order
     __syncthreads();
     unsigned long long* out = table + (size_t)si * stride;
     const int n = nValid;
@@ -182,7 +191,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                                                                  unsigned long long* scratch, uint8_t* __restrict__ flags,
                                                                  int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters) {
     __shared__ BinShared s_all[kBinWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-read (S2R) inside the loops
     BinShared& S = s_all[warp];
     unsigned long long* list = scratch + (size_t)(blockIdx.x * kBinWarps + warp) * stride;
     unsigned long long myRays = 0, myEntries = 0;
@@ -247,68 +258,79 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
             float bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zcull : 0.f;
             TileGeom tg;
             tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
-            bool inited = false, tileHit = false, done = !occupied || L == 0;
-            int pend = 0, myTri = 0, base = 0;
-            unsigned m = 0;
-            unsigned long long e = 0ull;
-            float zl = 0.f;
-            for (;;) {
-                // ---- next leaf whose rectangle contains the tile ----
-                bool have = false;
-                int first = 0, cnt = 0;
-                while (!done && !have) {
-                    const float bound = zcull * 1.000001f + 1e-4f;
-                    if (m == 0u) {
-                        if (base >= L) { done = true; break; }
-                        const int i = base + lane;
-                        e = i < L ? list[i] : kNoEntry;
-                        zl = (float)(unsigned)(e >> 48) * iq;
-                        // sorted by depth: when the first entry of the chunk is behind the farthest hit, so is everything after it
-                        if (__shfl_sync(0xffffffffu, zl, 0) > bound) { done = true; break; }
-                        const unsigned r = (unsigned)(e >> 28);
-                        const int tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
-                        m = __ballot_sync(0xffffffffu, i < L && tx0 <= tx && tx <= tx1 && ty0 <= ty && ty <= ty1 && zl <= bound);
-                        base += 32;
-                        myEntries += 32ull;
-                        continue;
+            bool inited = false, tileHit = false;
+            // Triangles wait in lane order: lanes < pend carry one each (myTri, its leaf's depth myZ) from the previous chunk.
+            int pend = 0, myTri = 0;
+            float myZ = 0.f;
+            // ---- flush: set up to 32 triangles up in parallel, one per lane, then test them one after the other ----
+            auto flush = [&](bool mineValid) {
+                __syncwarp();
+                bool mineOk = false;
+                if (mineValid) mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
+                const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
+                if (live) {
+                    if (!inited) {
+                        tile_init(S.t, S.id, lane, vw, vh, zFar);
+                        inited = true;
                     }
-                    const int k = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (__shfl_sync(0xffffffffu, zl, k) > bound) { m = 0u; continue; }  // later entries of the chunk are farther still
-                    const unsigned ref = __shfl_sync(0xffffffffu, (unsigned)e, k) & 0x0fffffffu;
-                    first = (int)(ref >> kLeafShift);
-                    cnt = (int)(ref & kLeafMask);
-                    have = true;
-                }
-                if ((have && pend + cnt > kPending) || (done && pend > 0)) {
-                    // ---- flush: set the pending triangles up in parallel, one per lane, then test them one after the other ----
                     __syncwarp();
-                    bool mineOk = false;
-                    if (lane < pend) mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
-                    const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
-                    myTris += pend;
-                    pend = 0;
-                    if (live) {
-                        if (!inited) {
-                            tile_init(S.t, S.id, lane, vw, vh, zFar);
-                            inited = true;
-                        }
+                    const bool dirty = raster_staged(live, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
+                    if (__any_sync(0xffffffffu, dirty)) {
+                        tileHit = true;
                         __syncwarp();
-                        const bool dirty = raster_staged(live, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
-                        if (__any_sync(0xffffffffu, dirty)) {
-                            tileHit = true;
-                            __syncwarp();
-                            refresh_depth_bounds(S.t, lane, bzReg, zcull);
-                        }
+                        refresh_depth_bounds(S.t, lane, bzReg, zcull);
                     }
                 }
-                if (have) {
-                    if (lane >= pend && lane < pend + cnt) myTri = first + lane - pend;
-                    pend += cnt;
-                } else if (done) {
-                    break;
+            };
+            for (int base = 0; occupied && base < L; base += 32) {
+                float bound = zcull * 1.000001f + 1e-4f;
+                const int i = base + lane;
+                const unsigned long long e = i < L ? list[i] : kNoEntry;
+                const float zl = (float)(unsigned)(e >> 48) * iq;
+                // sorted by depth: when the first entry of the chunk is behind the farthest hit, so is everything after it
+                if (__shfl_sync(0xffffffffu, zl, 0) > bound) break;
+                myEntries += 32ull;
+                const unsigned r = (unsigned)(e >> 28);
+                const int tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
+                const bool hit = i < L && tx0 <= tx && tx <= tx1 && ty0 <= ty && ty <= ty1 && zl <= bound;
+                if (!__any_sync(0xffffffffu, hit)) continue;
+                // the triangles of the leaves that contain the tile, in list order: leaf k contributes positions [P_k, P_k + cnt_k)
+                const int first = (int)(((unsigned)e & 0x0fffffffu) >> kLeafShift);
+                const int cnt = hit ? (int)((unsigned)e & kLeafMask) : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+                for (int q = 0; q < cnt; ++q) S.queue[incl - cnt + q] = (uint8_t)((lane << 3) | q);  // (source lane, triangle of its leaf)
+                __syncwarp();
+                const int pend0 = pend, avail = pend0 + total;
+                myTris += total;
+                // position p of the waiting line: p < pend is lane p's carried triangle, otherwise queue[p - pend]
+                int p = lane;
+                for (; p - lane + 32 <= avail; p += 32) {
+                    const int qp = p - pend0;
+                    const unsigned b = qp >= 0 ? S.queue[qp] : 0u;
+                    const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
+                    const float z = __shfl_sync(0xffffffffu, zl, b >> 3);
+                    if (qp >= 0) { myTri = tri; myZ = z; }
+                    flush(myZ <= bound);  // a flush may have pulled the farthest hit in front of this leaf since it was queued
+                    bound = zcull * 1.000001f + 1e-4f;
+                }
+                {   // what is left waits in lanes 0 .. avail - (p - lane) - 1
+                    const int qp = p - pend0;
+                    const bool take = p < avail && qp >= 0;
+                    const unsigned b = take ? S.queue[qp] : 0u;
+                    const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
+                    const float z = __shfl_sync(0xffffffffu, zl, b >> 3);
+                    if (take) { myTri = tri; myZ = z; }
+                    pend = avail - (p - lane);
                 }
             }
+            if (pend > 0) flush(lane < pend && myZ <= zcull * 1.000001f + 1e-4f);
             __syncwarp();
             // ---- the winners ----
             if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
@@ -330,8 +352,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
 template <int THREADS, int ITEMS>
 void launch_leaf_table_t(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, int nSnaps, const BinBuffers& b,
                          cudaStream_t st) {
-    using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS>;
-    const size_t smem = sizeof(typename Sort::TempStorage);
+    using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS, cub::NullType, kSortRadixBits>;
+    const size_t smem = std::max(sizeof(typename Sort::TempStorage), (size_t)THREADS * ITEMS * sizeof(unsigned long long));
     static bool configured = false;
     if (!configured) {
         IPP_CUDA_CHECK(cudaFuncSetAttribute(k_leaf_table<THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -358,21 +380,28 @@ int bins_grid_blocks() {
 }
 int bins_warps_per_block() { return kBinWarps; }
 
-// stride of a pose's table: the leaf count rounded up to what the sort tile of its size class holds
+// size classes of the per-pose sort (threads x keys per thread); stride of a pose's table = capacity of its class
+struct SortClass { int capacity; };
+static const int kSortCaps[] = {1024, 2048, 3072, 4096, 6144, 8192, 12288, 16384};
 int bins_table_stride(int nLeaves) {
-    if (nLeaves <= 1024) return 1024;
-    if (nLeaves <= 4096) return 4096;
-    if (nLeaves <= 8192) return 8192;
+    for (int c : kSortCaps)
+        if (nLeaves <= c) return c;
     return kMaxBinLeaves;
 }
 
 void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, int nSnaps, const BinBuffers& b,
                        cudaStream_t st) {
     if (nSnaps <= 0) return;
-    if (sc.nLeaves <= 1024) launch_leaf_table_t<256, 4>(sc, cam, d_snaps, nSnaps, b, st);
-    else if (sc.nLeaves <= 4096) launch_leaf_table_t<256, 16>(sc, cam, d_snaps, nSnaps, b, st);
-    else if (sc.nLeaves <= 8192) launch_leaf_table_t<512, 16>(sc, cam, d_snaps, nSnaps, b, st);
-    else launch_leaf_table_t<1024, 16>(sc, cam, d_snaps, nSnaps, b, st);
+    switch (bins_table_stride(sc.nLeaves)) {
+        case 1024: launch_leaf_table_t<256, 4>(sc, cam, d_snaps, nSnaps, b, st); break;
+        case 2048: launch_leaf_table_t<256, 8>(sc, cam, d_snaps, nSnaps, b, st); break;
+        case 3072: launch_leaf_table_t<256, 12>(sc, cam, d_snaps, nSnaps, b, st); break;
+        case 4096: launch_leaf_table_t<256, 16>(sc, cam, d_snaps, nSnaps, b, st); break;
+        case 6144: launch_leaf_table_t<512, 12>(sc, cam, d_snaps, nSnaps, b, st); break;
+        case 8192: launch_leaf_table_t<512, 16>(sc, cam, d_snaps, nSnaps, b, st); break;
+        case 12288: launch_leaf_table_t<1024, 12>(sc, cam, d_snaps, nSnaps, b, st); break;
+        default: launch_leaf_table_t<1024, 16>(sc, cam, d_snaps, nSnaps, b, st); break;
+    }
 }
 
 void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_superOffset, int nSnaps,
