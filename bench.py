@@ -268,7 +268,7 @@ def run_gpu(args):
         step_resident(s)
     barrier()
     ev.counters(reset=True)
-    for k in range(5):
+    for k in range(6):
         ev.kernel_time(k, reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -287,7 +287,10 @@ def run_gpu(args):
     vis_ms, vis_n = ev.kernel_time(1)
     red_ms, red_n = ev.kernel_time(0)
     col_ms, col_n = ev.kernel_time(2)
+    tab_ms, tab_n = ev.kernel_time(5)
+    variant = ev.visibility_variant()
     rays_total = allsum(cnt["rays"])
+    allsum_snap = allsum(cnt["snapshots"])
     fit_resident = np.zeros((world * POP, 4))
     d_fit.download(fit_resident)
 
@@ -362,8 +365,9 @@ def run_gpu(args):
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # K4 reads 64 B per BVH node a tile packet fetches and 48 B per triangle it stages; both counts are data
-    # dependent and come from the kernel's own device counters for exactly the timed launches.
+    # K4 reads 8 B per leaf-bin entry it scans (BVH variant: 64 B per node a tile packet fetches) and 48 B per triangle it stages
+    # (DESIGN.md section 4); the counts are data dependent and come from the kernel's own device counters for exactly the timed
+    # launches ("nodes" is in 64-byte units for either variant).
     alg_bytes_launch = (64.0 * vstat["nodes"] + 48.0 * vstat["triangles"]) / max(1, vis_n)
     rays_launch = cnt["rays"] / max(1, vis_n)
     vis_launch_s = vis_ms / max(1, vis_n) * 1e-3
@@ -381,21 +385,25 @@ def run_gpu(args):
                    "viewpoints_per_plan": VIEWPOINTS, "l2": "flushed every step (256 MiB write)", "seed": SEED,
                    "dtype_note": "visibility in f32 with f64 camera bases and f64-derived normals; energy, collision prisms and area sums in f64"},
         "rays_per_s": rays_total / (ms_total * 1e-3),
+        "rays_note": "pixel-centre rays of the 32x32 tiles actually rasterised; tiles the leaf tables prove empty issue none",
+        "pixels_resolved_per_s": allsum_snap * SPECS[3] * SPECS[3] / (ms_total * 1e-3),
         "snapshots_per_step": cnt["snapshots"] / args.steps, "edges_rendered_per_step": cnt["edges_rendered"] / args.steps,
-        "kernel_ms_per_step": {"edge_visibility": vis_ms / args.steps, "plan_reduce": red_ms / args.steps, "edge_collision": col_ms / args.steps},
+        "kernel_ms_per_step": {"edge_visibility": vis_ms / args.steps, "leaf_tables": tab_ms / args.steps, "plan_reduce": red_ms / args.steps,
+                               "edge_collision": col_ms / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pop_total * VIEWPOINTS * 4 + (pop_total + 1) * 8),
                 "d2h_bytes_per_step": int(pop_total * 4 * 8), "ms_per_step": ms_e2e / args.steps, "matches_resident_path": bool(same)},
         "gpu_launches": int(cnt["launches"]),
-        "roofline": {"kernel": "k_visibility", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+        "roofline": {"kernel": "k_visibility_bins" if variant == "bins" else "k_visibility", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": None, "algorithmic_bytes_per_launch": alg_bytes_launch, "us_per_launch": vis_launch_s * 1e6,
-                     "tiles_per_launch": vstat["tiles"] / max(1, vis_n), "nodes_per_tile": vstat["nodes"] / max(1, vstat["tiles"]),
+                     "tiles_per_launch": vstat["tiles"] / max(1, vis_n), "accel_64B_units_per_tile": vstat["nodes"] / max(1, vstat["tiles"]),
                      "triangles_per_tile": vstat["triangles"] / max(1, vstat["tiles"]), "rays_per_launch": rays_launch,
                      "peak_source": peak_src,
                      "survey_independent_ray_model": {"bytes_per_ray": b_ray, "gbs": rays_launch * b_ray / vis_launch_s / 1e9 if vis_launch_s > 0 else 0.0,
-                                                      "note": "what 1024 independent rays per tile would have requested; the tile packet shares the descent"},
-                     "note": "bytes = 64 B per BVH node fetched + 48 B per triangle staged, counted on the device; the 1.7 MB BVH + 1.3 MB "
-                             "triangles stay in L1/L2 (ncu: DRAM traffic in profiles/), the kernel is issue/latency bound, not HBM bound"},
+                                                      "note": "what one independent BVH descent per issued ray would have requested; a tile shares one leaf list"},
+                     "note": "bytes = 8 B per leaf-bin entry scanned (64 B per BVH node in the bvh variant) + 48 B per triangle staged, counted "
+                             "on the device; triangles and leaf tables are served from L1/L2 (ncu DRAM traffic in profiles/), the kernel is "
+                             "instruction-issue bound, not HBM bound"},
         "roofline_plan_reduce": warm,
     }
     # CPU baseline beside it: the CPU restatement on this box's host cores, bounded sample
@@ -413,7 +421,7 @@ def run_gpu(args):
     if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")):
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            line["roofline"]["traffic"] = tr.get("k_visibility_dram_bytes_per_launch")
+            line["roofline"]["traffic"] = tr.get(line["roofline"]["kernel"] + "_dram_bytes_per_launch")
             line["roofline"]["traffic_source"] = tr.get("source")
         except (OSError, ValueError):
             pass
