@@ -127,6 +127,8 @@ int ipp_render_ids(ipp_t* h, const double* eye3, const double* center3, const do
  * [depth:16 | tx0:5 tx1:5 ty0:5 ty1:5 | first triangle:24 count:4], *count = entries of the pose, out_tile_mask32 = occupied tiles */
 int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,
                    uint32_t* out_tile_mask32);
+/* triangle id (file order) at every position of the BVH-ordered triangle arrays: out_T[position] = id */
+int ipp_bvh_order(ipp_t* h, int32_t* out_T);
 /* BVH self-check: closest-hit of n rays (origin xyz, dir xyz) through the BVH and by brute force; returns
  * the number of mismatching ids */
 int ipp_bvh_selftest(ipp_t* h, const float* rays_nx6, int64_t n, int32_t* out_ids, int64_t* mismatches);

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "ipp_boxes_hit_mesh": (C.c_int, [H, c_f64p, C.c_int64, C.c_double, c_u8p]),
     "ipp_render_ids": (C.c_int, [H, c_f64p, c_f64p, c_f64p, c_i32p]),
     "ipp_leaf_table": (C.c_int, [H, c_f64p, c_f64p, c_f64p, C.POINTER(C.c_uint64), C.c_int64, c_i64p, c_u32p]),
+    "ipp_bvh_order": (C.c_int, [H, c_i32p]),
     "ipp_bvh_selftest": (C.c_int, [H, c_f32p, C.c_int64, c_i32p, c_i64p]),
     "ipp_bvh_selftest_ex": (C.c_int, [H, c_f32p, C.c_int64, c_i32p, c_i32p, c_f32p, c_i64p]),
     "ipp_device_alloc": (C.c_int, [H, C.c_int64, C.POINTER(C.c_void_p)]),

@@ -270,6 +270,12 @@ class PlanCoverageEstimator(object):
                 "ty1": ((k >> np.uint64(28)) & np.uint64(31)).astype(np.int64), "first": ((k >> np.uint64(4)) & np.uint64(0xFFFFFF)).astype(np.int64),
                 "cnt": (k & np.uint64(15)).astype(np.int64), "tile_mask": mask}
 
+    def bvh_order(self):
+        """Triangle id (file order) at every position of the BVH-ordered triangle arrays."""
+        out = np.zeros(self.T, dtype=np.int32)
+        _lib.check(self._L.ipp_bvh_order(self._h, out.ctypes.data_as(_lib.c_i32p)))
+        return out
+
     def bvh_selftest_ex(self, rays):
         r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 6)
         ids = np.zeros(r.shape[0], dtype=np.int32)

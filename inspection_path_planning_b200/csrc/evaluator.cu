@@ -721,6 +721,14 @@ void Evaluator::leafTable(const double* eye, const double* center, const double*
     sync();
 }
 
+void Evaluator::bvhOrder(int32_t* out) {
+    bind();
+    std::vector<float4> a(scene_.T);
+    if (scene_.T > 0) IPP_CUDA_CHECK(cudaMemcpyAsync(a.data(), scene_.ta, (size_t)scene_.T * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    for (int i = 0; i < scene_.T; ++i) memcpy(out + i, &a[i].w, 4);
+}
+
 void Evaluator::bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute, float* outT) {
     bind();
     *mismatches = 0;

@@ -44,6 +44,7 @@ class Evaluator {
     void boxesHitMesh(const double* centres, int64_t n, double half, uint8_t* out);
     void renderIds(const double* eye, const double* center, const double* up, int32_t* out);
     void leafTable(const double* eye, const double* center, const double* up, uint64_t* out, int64_t cap, int64_t* count, uint32_t* mask32);
+    void bvhOrder(int32_t* out);
     void bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute = nullptr, float* outT = nullptr);
 
     // ---- plumbing ----

@@ -275,6 +275,11 @@ int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const do
     E(h).leafTable(eye3, center3, up3, out, cap, count, out_tile_mask32);
     IPP_CATCH
 }
+int ipp_bvh_order(ipp_t* h, int32_t* out_T) {
+    IPP_TRY
+    E(h).bvhOrder(out_T);
+    IPP_CATCH
+}
 int ipp_visibility_variant(ipp_t* h, int use_bins, int* out_active) {
     IPP_TRY
     if (use_bins >= 0) E(h).setUseBins(use_bins != 0);

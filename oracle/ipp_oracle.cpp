@@ -810,6 +810,23 @@ struct Oracle {
         return true;
     }
 
+    // the same with the triangle dilated by r (image-plane units): every edge function, normalised by its gradient, may be short
+    // of zero by r.  Used for the lenient class only: a sliver thinner than the sample displacement can lie between the five
+    // sample positions and still be the rightful owner of a pixel whose centre is within rounding of its edge.
+    static inline bool frag_dilated(const Setup& S, double X, double Y, double r, double& t) {
+        double eu = S.na[0] * X + S.na[1] * Y + S.na[2];
+        double ev = S.nb[0] * X + S.nb[1] * Y + S.nb[2];
+        double ew = S.nc[0] * X + S.nc[1] * Y + S.nc[2];
+        double gu = std::sqrt(S.na[0] * S.na[0] + S.na[1] * S.na[1]), gv = std::sqrt(S.nb[0] * S.nb[0] + S.nb[1] * S.nb[1]),
+               gw = std::sqrt(S.nc[0] * S.nc[0] + S.nc[1] * S.nc[1]);
+        double det = eu + ev + ew;
+        if (det == 0) return false;
+        bool pos = eu >= -r * gu && ev >= -r * gv && ew >= -r * gw, neg = eu <= r * gu && ev <= r * gv && ew <= r * gw;
+        if (!pos && !neg) return false;
+        t = S.vol / det;
+        return true;
+    }
+
     void render(const V3& eye, const V3& center, const V3& up, Bits& seen, Bits* strictSeen, Bits* lenientSeen) {
         nSnapshots++;
         nPixels += (uint64_t)imgW * imgH;
@@ -864,6 +881,13 @@ struct Oracle {
                     for (int px = S.x0; px <= S.x1; ++px) {
                         double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
                         size_t pix = ((size_t)py * W + px) * K;
+                        if (pass == 1) {
+                            // lenient, continuum form: the pixel centre within eps_px of the triangle and the depth inside the
+                            // widened band of the nearest surface there
+                            double t;
+                            if (frag_dilated(S, X, Y, std::max(ex, ey) * 1.5, t) && t >= lenLo && t <= lenHi && t <= z1[pix] * bandWide)
+                                bits_set(*lenientSeen, i);
+                        }
                         for (int k = 0; k < K; ++k) {
                             double t;
                             if (!frag(S, X + offx[k], Y + offy[k], t)) continue;

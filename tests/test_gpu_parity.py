@@ -333,3 +333,86 @@ def test_ragged_and_degenerate_plans(sphere):
     assert got[0].tolist() == [1.0, 0.0, 0.0, 0.0]
     with pytest.raises(IndexError):
         g.evaluatePopulation([[[0], [492]]], True, True)
+
+
+# ------------------------------------------------------------------ the two K4 variants (leaf bins / BVH walk per tile)
+@pytest.mark.parametrize("fx", ["sphere", "mockup256", "luis1"])
+def test_default_variant_is_the_binned_kernel(fx, request):
+    g, _ = request.getfixturevalue(fx)
+    assert g.visibility_variant() == "bins"
+
+
+@pytest.mark.parametrize("fx,n", [("sphere", 8), ("mockup256", 8), ("luis1", 8)])
+def test_bvh_walk_variant_parity_and_agreement(fx, n, request):
+    """The BVH-walking kernel (the path of meshes too large for the leaf tables) meets the same bar as the binned one, and the
+    two differ from each other by no more than the flip budget (the order of depth ties is the only difference)."""
+    g, o = request.getfixturevalue(fx)
+    rng = np.random.default_rng(33)
+    N = o.getNumberOfBoxes()
+    stats = dict(flips=0, edges=0, seen=0, outside=0)
+    try:
+        for _ in range(n):
+            prev, curr = (int(x) for x in rng.choice(N, 2, replace=False))
+            assert g.visibility_variant(True) == "bins"
+            bins = g.edge_bitmap(prev, curr)
+            assert g.visibility_variant(False) == "bvh"
+            nflip, outside = _check_edge(g, o, prev, curr, stats)
+            bvh = g.edge_bitmap(prev, curr)
+            assert nflip <= max(1, int(FLIP_BUDGET * o.T)) and outside == 0, (prev, curr, stats)
+            assert popcount(bins ^ bvh) <= max(1, int(FLIP_BUDGET * o.T))
+        # images through the BVH walk
+        tot = bad = 0
+        for eye, tgt, up in _poses(o, rng, 3):
+            a, b = g.render_ids(eye, tgt, up), o.render_ids(eye, tgt, up)
+            tot += a.size
+            bad += int((a != b).sum())
+        assert bad / tot < 2e-3, (bad, tot)
+    finally:
+        g.visibility_variant(True)
+
+
+@pytest.mark.parametrize("fx", ["sphere", "mockup256", "luis1"])
+def test_leaf_table_is_sorted_and_covers_every_visible_pixel(fx, request):
+    g, o = request.getfixturevalue(fx)
+    rng = np.random.default_rng(34)
+    w, h = g.image_size()
+    for eye, tgt, up in _poses(o, rng, 4):
+        t = g.leaf_table(eye, tgt, up)
+        n = t["count"]
+        assert n == len(t["zq"])
+        assert np.all(np.diff(t["zq"]) >= 0)  # front to back
+        assert np.all(t["tx0"] <= t["tx1"]) and np.all(t["ty0"] <= t["ty1"])
+        assert np.all((t["cnt"] >= 1) & (t["cnt"] <= 8)) and np.all(t["first"] + t["cnt"] <= g.T)
+        img = g.render_ids(eye, tgt, up)
+        ys, xs = np.nonzero(img >= 0)
+        # every pixel that shows a triangle lies in a tile of the occupancy mask
+        mask = t["tile_mask"]
+        assert np.all((mask[ys // 32] >> (xs // 32).astype(np.uint32)) & 1)
+        # ... and inside the rectangle of a leaf that holds that triangle (checked on a sample of pixels)
+        if len(ys):
+            pick = rng.choice(len(ys), size=min(200, len(ys)), replace=False)
+            pos = np.empty(g.T, dtype=np.int64)
+            pos[g.bvh_order()] = np.arange(g.T)
+            for k in pick:
+                p = pos[img[ys[k], xs[k]]]
+                leaf = np.nonzero((t["first"] <= p) & (p < t["first"] + t["cnt"]))[0]
+                assert len(leaf) == 1
+                j = leaf[0]
+                assert t["tx0"][j] <= xs[k] // 32 <= t["tx1"][j] and t["ty0"][j] <= ys[k] // 32 <= t["ty1"][j]
+
+
+def test_population_fitness_identical_across_variants_up_to_ties(mockup256):
+    g, o = mockup256
+    rng = np.random.default_rng(35)
+    plans = random_plans(rng, o.getNumberOfBoxes(), 10, (2, 5))
+    try:
+        g.visibility_variant(False)
+        g.clear_memo()
+        a, _ = _compare_population(g, o, plans, memo=True, no_limit=True)
+        g.visibility_variant(True)
+        g.clear_memo()
+        b, _ = _compare_population(g, o, plans, memo=True, no_limit=True)
+        assert np.array_equal(a[:, 1:], b[:, 1:])
+    finally:
+        g.visibility_variant(True)
+        g.clear_memo()

@@ -18,12 +18,16 @@ g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), specs(H))
 o = Oracle(mesh_path(mesh), specs(H))
 if len(sys.argv) > 5:
     o.set_margins(float(sys.argv[4]), float(sys.argv[5]))
-rng = np.random.default_rng(31)
+rng = np.random.default_rng(int(os.environ.get("SEED", "31")))
+if os.environ.get("VARIANT"):
+    print("variant", g.visibility_variant(os.environ["VARIANT"] == "bins"))
+edges = [tuple(int(x) for x in e.split("-")) for e in os.environ.get("EDGES", "").split(",") if e]
 N = o.getNumberOfBoxes()
 area = o.areas()
 tot = dict(seen=0, flips=0, outside=0, darea=0.0)
-for _ in range(n):
-    prev, curr = (int(x) for x in rng.choice(N, 2, replace=False))
+for k in range(max(n, len(edges))):
+    prev, curr = edges[k] if k < len(edges) else (int(x) for x in rng.choice(N, 2, replace=False))
+    if edges and k >= len(edges): break
     got = g.edge_bitmap(prev, curr)
     seen, strict, lenient = o.edge_bitmap(prev, curr, classify=True)
     extra, missing = bit_ids(got & ~seen), bit_ids(seen & ~got)
