@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(THREADS) k_leaf_table(DeviceScene sc, CameraPa
         }
         const unsigned tx0 = px0 >> 5, tx1 = min(px1 >> 5, txMax), ty0 = py0 >> 5, ty1 = min(py1 >> 5, tyMax);
         // depth in 2^-12 steps of the culling range (the low 4 of the 16 key bits stay 0: fewer sort passes)
-        const unsigned zq = (unsigned)fminf(65534.f, floorf(fmaxf(zmin, 0.f) * qscale)) & 0xfff0u;
+        // (capped one step below the top: the 12 sorted bits of a real entry never equal those of the empty key)
+        const unsigned zq = min((unsigned)fminf(65534.f, floorf(fmaxf(zmin, 0.f) * qscale)) & 0xfff0u, 0xffe0u);
         const unsigned ref = (unsigned)__float_as_int(lo4.w) & 0x0fffffffu;
         stage[leaf] = ((unsigned long long)zq << 48) | ((unsigned long long)tx0 << 43) | ((unsigned long long)tx1 << 38) |
                    ((unsigned long long)ty0 << 33) | ((unsigned long long)ty1 << 28) | ref;

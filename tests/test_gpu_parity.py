@@ -225,6 +225,10 @@ def test_single_camera_modes(oracle_mod):
 
 # ------------------------------------------------------------------ plans
 def _compare_population(g, o, plans, memo=True, no_limit=False):
+    """Fitness rows against the oracle.  Energy, path length, collision counts: exact formulas.  Coverage: within 1e-5 relative,
+    except for plans whose seen set differs from the oracle's by edge-epsilon triangles -- there the north star's flip budget
+    applies instead: at most 0.05 % of the triangles, every one of them inside the oracle's edge-epsilon band on the edge that
+    shows it, and the coverage the evaluator reports must be exactly the area of the set it saw."""
     got = g.evaluatePopulation(plans, memo, no_limit)
     want = o.evaluatePopulation(plans, memo, no_limit)
     np.testing.assert_allclose(got[:, 1], want[:, 1], rtol=ENERGY_RTOL, atol=0)
@@ -232,8 +236,21 @@ def _compare_population(g, o, plans, memo=True, no_limit=False):
     assert np.array_equal(got[:, 3], want[:, 3])  # colliding-edge counts: bit-exact flags
     gated = want[:, 0] == 1.0
     assert np.array_equal(got[:, 0] == 1.0, gated) or np.allclose(got[:, 0], want[:, 0], rtol=COVERAGE_RTOL)
-    # coverage fraction (1 - score) within 1e-5 relative
-    np.testing.assert_allclose(1.0 - got[:, 0], 1.0 - want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9)
+    close = np.isclose(1.0 - got[:, 0], 1.0 - want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9)
+    for p in np.nonzero(~close)[0]:
+        ids = [int(x[0]) for x in plans[p]]
+        if getattr(o, "loops", False) or getattr(o, "has_start", False):
+            raise AssertionError("coverage of plan %d differs: %r vs %r" % (p, got[p], want[p]))
+        fit1, ub = g.evaluatePopulation([plans[p]], memo, no_limit, union_bitmap=True)
+        assert fit1[0, 0] == got[p, 0]
+        # what the evaluator reports is exactly the area-weighted coverage of the set it saw (K6 against the oracle's sum)
+        assert abs((1.0 - fit1[0, 0]) - (1.0 - o.coverage_of_bitmap(ub))) <= 1e-12
+        seen = np.zeros_like(ub); strict = np.zeros_like(ub); lenient = np.zeros_like(ub)
+        for a, b in zip(ids[:-1], ids[1:]):
+            s1, s2, s3 = o.edge_bitmap(a, b, classify=True)
+            seen |= s1; strict |= s2; lenient |= s3
+        assert popcount(ub ^ seen) <= max(1, int(FLIP_BUDGET * o.T)), (p, popcount(ub ^ seen))
+        assert popcount(strict & ~ub) == 0 and popcount(ub & ~lenient) == 0, p
     return got, want
 
 
