@@ -1,7 +1,7 @@
 """Where does the GPU see triangle TRI on edge PREV->CURR, and what does the oracle see at those pixels?"""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import mesh_path, specs
 from inspection_path_planning_b200 import cpp_binding

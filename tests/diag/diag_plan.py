@@ -1,7 +1,7 @@
 """Per-edge flips of the plans of a seeded population against the oracle classes, both K4 variants."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import bit_ids, mesh_path, popcount, random_plans, specs
 from inspection_path_planning_b200 import cpp_binding

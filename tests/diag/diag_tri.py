@@ -1,7 +1,7 @@
 """Pixel-level comparison of GPU and oracle item buffers for the poses of one edge (debug aid)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import bit_ids, mesh_path, specs
 from inspection_path_planning_b200 import cpp_binding

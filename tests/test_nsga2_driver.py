@@ -1,0 +1,139 @@
+"""The caller side of the hot path: NSGA-II pieces restated from DEAP, the generational loop of
+plan_optimizer/optimize_coverage.py with one batched evaluator call per generation, and the result-store dictionaries."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import mesh_path
+from inspection_path_planning_b200 import optimize_coverage as oc
+
+
+def _ind(fit, genes=((1,), (2,))):
+    i = oc.Individual([list(g) for g in genes])
+    i.fitness = tuple(fit)
+    return i
+
+
+def test_dominance_minimises_both_objectives():
+    assert oc.dominates((0.2, 5.0), (0.3, 5.0))
+    assert oc.dominates((0.2, 4.0), (0.3, 5.0))
+    assert not oc.dominates((0.2, 6.0), (0.3, 5.0))
+    assert not oc.dominates((0.2, 5.0), (0.2, 5.0))
+
+
+def test_fronts_and_crowding_distance_known_answer():
+    pts = [(0.1, 9.0), (0.5, 5.0), (0.9, 1.0), (0.6, 6.0), (0.95, 9.5), (0.5, 5.0)]
+    pop = [_ind(p) for p in pts]
+    fronts = oc.sort_nondominated(pop)
+    assert [sorted(i.fitness for i in f) for f in fronts] == [[(0.1, 9.0), (0.5, 5.0), (0.5, 5.0), (0.9, 1.0)], [(0.6, 6.0)], [(0.95, 9.5)]]
+    front = [_ind(p) for p in [(0.0, 4.0), (1.0, 3.0), (2.0, 1.0), (4.0, 0.0)]]
+    oc.assign_crowding_dist(front)
+    d = [i.crowding_dist for i in front]
+    assert d[0] == float("inf") and d[3] == float("inf")
+    assert d[1] == pytest.approx((2.0 - 0.0) / 4.0 + (4.0 - 1.0) / 4.0)
+    assert d[2] == pytest.approx((4.0 - 1.0) / 4.0 + (3.0 - 0.0) / 4.0)
+
+
+def test_sel_nsga2_takes_whole_fronts_then_the_least_crowded():
+    pts = [(0.0, 4.0), (1.0, 3.0), (1.1, 2.9), (2.0, 1.0), (4.0, 0.0), (5.0, 5.0)]
+    pop = [_ind(p) for p in pts]
+    chosen = oc.sel_nsga2(pop, 4)
+    got = sorted(i.fitness for i in chosen)
+    assert (5.0, 5.0) not in got and (0.0, 4.0) in got and (4.0, 0.0) in got and len(got) == 4
+    # of the two crowded neighbours at most one survives
+    assert sum(f in got for f in [(1.0, 3.0), (1.1, 2.9)]) == 1
+
+
+def test_tournament_and_crossover():
+    rng = random.Random(3)
+    pop = [_ind((i / 10.0, 10.0 - i)) for i in range(8)]
+    oc.sel_nsga2(pop, len(pop))
+    out = oc.sel_tournament_dcd(pop, len(pop), rng)
+    assert len(out) == 8 and all(o in pop for o in out)
+    with pytest.raises(ValueError):
+        oc.sel_tournament_dcd(pop[:6], 6, rng)
+    a, b = oc.Individual([[1], [2], [3]]), oc.Individual([[7], [8], [9], [10], [11]])
+    before = sorted(g[0] for g in a + b)
+    oc.cx_messy_one_point(a, b, rng)
+    assert sorted(g[0] for g in a + b) == before and len(a) + len(b) == 8
+
+
+def test_pareto_front_keeps_only_non_dominated_and_no_duplicates():
+    pf = oc.ParetoFront()
+    pf.update([_ind((0.5, 5.0)), _ind((0.6, 6.0)), _ind((0.4, 7.0))])
+    assert sorted(i.fitness for i in pf) == [(0.4, 7.0), (0.5, 5.0)]
+    pf.update([_ind((0.5, 5.0)), _ind((0.3, 4.0))])
+    assert sorted(i.fitness for i in pf) == [(0.3, 4.0)]
+    assert oc.hypervolume_2d([(0.3, 4.0)], [1.0, 10.0]) == pytest.approx(0.7 * 6.0)
+    assert oc.hypervolume_2d([(0.2, 8.0), (0.6, 2.0)], [1.0, 10.0]) == pytest.approx(0.8 * 2.0 + 0.4 * 6.0)
+
+
+def test_cleanup_and_mutation_respect_the_reference_rules():
+    ind = oc.Individual([[3], [3], [4], [4], [4], [3]])
+    oc.clean_up_individual(ind)
+    assert [g[0] for g in ind] == [3, 4, 3]
+    p = oc.Parameters()
+    rng = random.Random(0)
+    short = oc.Individual([[1], [2]])
+    for _ in range(50):
+        oc.mutate_waypoints(short, 10, p, rng)
+        assert len(short) >= p.MIN_PLAN_SIZE
+    with pytest.raises(AttributeError):
+        oc.Parameters(NOT_A_PARAMETER=1)
+
+
+@pytest.fixture(scope="module")
+def sphere_run(oracle_mod, tmp_path_factory):
+    sp = list(oc.Parameters.SENSOR_PARAMETERS)
+    sp[3] = 64
+    params = oc.Parameters(NUM_INDIVS=16, NUM_GENERATIONS=4, SENSOR_PARAMETERS=sp)
+    ev = oracle_mod.Oracle(mesh_path("sphere"), sp)
+    pop, pf, logbook, stats = oc.run_nsga2(ev, params, seed=11)
+    return ev, params, pop, pf, logbook, stats, tmp_path_factory.mktemp("run")
+
+
+def test_generational_loop_with_the_cpu_evaluator(sphere_run, oracle_mod):
+    ev, params, pop, pf, logbook, stats, _ = sphere_run
+    assert len(pop) == params.NUM_INDIVS and len(logbook) == params.NUM_GENERATIONS + 1
+    assert all(len(i) >= params.MIN_PLAN_SIZE for i in pop)
+    # fitness values are the evaluator's own answers for the stored genotypes
+    for ind in pop[:6]:
+        assert tuple(ev.evaluatePlan(list(ind), True, 3, False)) == pytest.approx(ind.fitness)
+    # the front is mutually non-dominated and the memo was trimmed to the population once per generation
+    fits = [i.fitness for i in pf]
+    assert not any(oc.dominates(a, b) for a in fits for b in fits)
+    assert stats["calls"] <= 3 + params.NUM_GENERATIONS + 10 and stats["memoised_edges"] == ev.memo_size()
+    # same seed, same run
+    ev2 = oracle_mod.Oracle(mesh_path("sphere"), params.SENSOR_PARAMETERS)
+    pop2, pf2, _, _ = oc.run_nsga2(ev2, params, seed=11)
+    assert [list(i) for i in pop2] == [list(i) for i in pop] and [i.fitness for i in pop2] == [i.fitness for i in pop]
+
+
+def test_result_stores_use_the_reference_keys(sphere_run):
+    ev, params, pop, pf, _, stats, out = sphere_run
+    for name in ("winner_indivs.yml", "winner_indivs.pkl"):
+        path = oc.store_population_and_parameters(pop, name, str(out), "sphere.obj", params, ev, pf, 1.5, stats["memoised_edges"])
+        d = oc.load_dumped_population(path)
+        assert set(d) == {"population", "scene", "plan_origin", "sensor_params", "pareto_front", "max_energy", "num_memoized_solutions",
+                          "elapsed_time", "plan_loops_around"}
+        assert len(d["population"]) == len(pop) and d["population"][0]["genotype1"] == [list(g) for g in pop[0]]
+        assert d["population"][0]["fitness_weights"] == [-1, -1] and d["max_energy"] == ev.getMaxAllowedEnergy()
+        assert len(d["pareto_front"]) == len(pf)
+
+
+@pytest.mark.gpu
+def test_generational_loop_on_the_gpu_matches_the_cpu_evaluator(sphere_run):
+    from inspection_path_planning_b200 import cpp_binding
+    ev, params, pop, pf, logbook, stats, _ = sphere_run
+    g = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), params.SENSOR_PARAMETERS)
+    try:
+        gpop, gpf, glog, gstats = oc.run_nsga2(g, params, seed=11)
+        # generation 0 is evaluated on identical genotypes: energies agree to rounding, scores within the flip budget's area
+        assert glog[0]["fit_min"][1] == pytest.approx(logbook[0]["fit_min"][1], rel=1e-12)
+        assert glog[0]["fit_avg"][0] == pytest.approx(logbook[0]["fit_avg"][0], abs=2e-3)
+        assert gstats["calls"] == stats["calls"] or abs(gstats["evaluations"] - stats["evaluations"]) < 64
+        fits = [i.fitness for i in gpf]
+        assert not any(oc.dominates(a, b) for a in fits for b in fits)
+    finally:
+        g.close()
