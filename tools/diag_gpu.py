@@ -21,11 +21,11 @@ g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), specs(H))
 print("setup %.3fs T=%d N=%d maxE=%.6f" % (time.time() - t, g.T, g.getNumberOfBoxes(), g.getMaxAllowedEnergy()), flush=True)
 rng = np.random.default_rng(20261019)
 plans = cpp_binding.pack_population(random_plans(rng, g.getNumberOfBoxes(), pop, V))
-names = ["reduce", "visibility", "collision", "pack", "plan"]
+names = ["reduce", "visibility", "collision", "pack", "plan", "table"]
 for it in range(3):
     g.counters(reset=True)
     g.visibility_stats(reset=True)
-    for k in range(5):
+    for k in range(6):
         g.kernel_time(k, reset=True)
     t = time.time()
     fit = g.evaluatePopulation(plans, True, True)
@@ -34,7 +34,7 @@ for it in range(3):
     vs = g.visibility_stats()
     if vs["tiles"]:
         print("   per tile: nodes %.1f triangles %.1f (tiles %d)" % (vs["nodes"] / vs["tiles"], vs["triangles"] / vs["tiles"], vs["tiles"]), flush=True)
-    kt = {names[k]: g.kernel_time(k) for k in range(5)}
+    kt = {names[k]: g.kernel_time(k) for k in range(6)}
     print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  counters %s" % (it, dt, pop / dt, (1 - fit[:, 0]).mean(), c), flush=True)
     print("   kernel ms:", {k: (round(v[0], 3), v[1]) for k, v in kt.items()}, flush=True)
     if c["rays"]:
