@@ -137,3 +137,28 @@ def test_generational_loop_on_the_gpu_matches_the_cpu_evaluator(sphere_run):
         assert not any(oc.dominates(a, b) for a in fits for b in fits)
     finally:
         g.close()
+
+
+def test_plan_export_yaml_follows_the_rock_format(sphere_run):
+    import math
+    import yaml
+    from inspection_path_planning_b200 import plan_exporter as pe
+    ev, params, pop, pf, _, stats, out = sphere_run
+    plan = [list(g) for g in max(pop, key=len)]
+    pos, heads = ev.interpretAndExportPlan(plan)
+    path = pe.export_plan_to_yaml(ev, plan, str(out / "plan_0.yml"), position_offsets=(35.0, -10.0, -15.0))
+    d = yaml.safe_load(open(path))
+    wps = d["waypoints"]
+    assert len(wps) == len(pos) == len(heads) + 1
+    assert wps[0]["orientation"] == {"r": 0.0, "p": 0.0, "y": 0.0}
+    for k, w in enumerate(wps):
+        assert w["position"]["x"] == pytest.approx(pos[k][0] + 35.0) and w["position"]["z"] == pytest.approx(pos[k][2] - 15.0)
+        if k:
+            assert w["orientation"]["y"] == pytest.approx(math.atan2(heads[k - 1][1], heads[k - 1][0]))
+    # a quarter turn about +z turns every yaw by 90 degrees and maps (x, y) to (-y, x)
+    rot = pe.plan_to_waypoints(ev, plan, rotation_degrees_around_z=90.0)
+    base = pe.plan_to_waypoints(ev, plan)
+    assert rot[1]["position"]["x"] == pytest.approx(-base[1]["position"]["y"]) and rot[1]["position"]["y"] == pytest.approx(base[1]["position"]["x"])
+    dy = (rot[1]["orientation"]["y"] - base[1]["orientation"]["y"] - math.pi / 2 + math.pi) % (2 * math.pi) - math.pi
+    assert abs(dy) < 1e-9
+    assert pe.plan_to_waypoints(ev, []) == []
