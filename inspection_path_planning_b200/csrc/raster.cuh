@@ -30,6 +30,14 @@ __device__ __forceinline__ double ddot(double ax, double ay, double az, double b
     return __fma_rn(az, bz, __fma_rn(ay, by, __dmul_rn(ax, bx)));
 }
 
+// MUFU.RCP without the range scaling __fdividef wraps around it (4 instructions per division): a denormal determinant flushes to
+// zero, the depth becomes inf / NaN and fails the range test like an exactly grazing ray does.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Per-tile constants of one lane: pixel-centre image-plane coordinates X(px) = ((px + 0.5) / W * 2 - 1) tanX = px kx + cx.
 struct TileGeom {
     float kx8, ky4;      // image-plane step between 8x4 blocks
@@ -155,8 +163,8 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
                         ew1 = __fmaf_rn(ecs, X1, __fmaf_rn(ecu, Y1, ecf));
             const bool in0 = fminf(fminf(eu0, ev0), ew0) >= 0.f;         // the ray crosses the triangle
             const bool in1 = two && fminf(fminf(eu1, ev1), ew1) >= 0.f;
-            const float t0 = __fdividef(vol, gs * X0 + (gu * Y0 + gf));  // det == 0: inf / NaN fails the range test
-            const float t1 = __fdividef(vol, gs * X1 + (gu * Y1 + gf));
+            const float t0 = vol * rcp_approx(gs * X0 + (gu * Y0 + gf));  // det == 0: inf / NaN fails the range test
+            const float t1 = vol * rcp_approx(gs * X1 + (gu * Y1 + gf));
             const int idx0 = blk0 * 32 + lane, idx1 = blk1 * 32 + lane;
             const float ht0 = St[idx0], ht1 = St[idx1];
             // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins

@@ -433,3 +433,25 @@ def test_population_fitness_identical_across_variants_up_to_ties(mockup256):
     finally:
         g.visibility_variant(True)
         g.clear_memo()
+
+
+def test_non_square_sensor_and_small_images(oracle_mod):
+    """W != H (aspect = specs[2] / specs[1], the reference's argument swap), images smaller than one supertile, one camera only."""
+    from inspection_path_planning_b200 import cpp_binding
+    for sp in ([2.0, 60, 46, 96, 0.1, 10, 1, 1], [1.5, 40, 55, 130, 0.2, 8, 1, 0], [2.0, 46, 46, 40, 0.1, 10, 0, 1]):
+        g = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), sp)
+        o = oracle_mod.Oracle(mesh_path("sphere"), sp)
+        try:
+            assert g.image_size() == o.image_size()
+            rng = np.random.default_rng(51)
+            N = o.getNumberOfBoxes()
+            stats = dict(flips=0, edges=0, seen=0, outside=0)
+            for _ in range(6):
+                prev, curr = (int(x) for x in rng.choice(N, 2, replace=False))
+                for variant in (True, False):
+                    g.visibility_variant(variant)
+                    nflip, outside = _check_edge(g, o, prev, curr, stats)
+                    assert nflip <= 1 and outside == 0, (sp, prev, curr, variant, stats)
+            assert stats["seen"] > 0
+        finally:
+            g.close()
