@@ -167,6 +167,7 @@ Evaluator::Evaluator(const std::string& scenePath, const double specs[8], bool p
             maxSnapsPerBatch_ = std::max<int64_t>(64, std::min<int64_t>(maxSnapsPerBatch_, tableBudget / ((int64_t)bins_.stride * 8)));
         }
     }
+    if (const char* e = getenv("IPP_MAX_POSES_PER_BATCH")) maxSnapsPerBatch_ = std::max<int64_t>(1, std::min<int64_t>(maxSnapsPerBatch_, atoll(e)));
     d_countsAll_ = dalloc<int>(nKeys_ + 1);
     d_rows_ = dalloc<uint32_t>((size_t)(rowCapacity_ + 1) * rowWords_);
     d_freeStack_ = dalloc<int>(rowCapacity_);

@@ -455,3 +455,38 @@ def test_non_square_sensor_and_small_images(oracle_mod):
             assert stats["seen"] > 0
         finally:
             g.close()
+
+
+def test_render_batches_split_by_pose_budget_give_identical_results(monkeypatch):
+    """IPP_MAX_POSES_PER_BATCH forces the new edges of one call through many small render batches (the path a 100 k-plan
+    population takes when its leaf tables exceed the table budget): same fitness rows, bit for bit."""
+    from inspection_path_planning_b200 import cpp_binding
+    sp = specs(64)
+    rng = np.random.default_rng(61)
+    a = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), sp)
+    plans = random_plans(rng, a.getNumberOfBoxes(), 40, (2, 9))
+    want = a.evaluatePopulation(plans, True, True)
+    n_whole = a.counters()["launches"]
+    a.close()
+    monkeypatch.setenv("IPP_MAX_POSES_PER_BATCH", "37")
+    b = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), sp)
+    try:
+        got = b.evaluatePopulation(plans, True, True)
+        assert np.array_equal(got, want)
+        assert b.counters()["launches"] > n_whole  # really went through several batches
+    finally:
+        b.close()
+
+
+def test_images_above_1024_pixels_take_the_bvh_walk(oracle_mod):
+    from inspection_path_planning_b200 import cpp_binding
+    sp = specs(1100)
+    g = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), sp)
+    o = oracle_mod.Oracle(mesh_path("sphere"), sp)
+    try:
+        assert g.visibility_variant() == "bvh" and g.visibility_variant(True) == "bvh"  # the tables do not apply, the request is refused
+        stats = dict(flips=0, edges=0, seen=0, outside=0)
+        nflip, outside = _check_edge(g, o, 100, 101, stats)
+        assert nflip <= 1 and outside == 0 and stats["seen"] > 0
+    finally:
+        g.close()
