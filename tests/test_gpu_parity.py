@@ -490,3 +490,40 @@ def test_images_above_1024_pixels_take_the_bvh_walk(oracle_mod):
         assert nflip <= 1 and outside == 0 and stats["seen"] > 0
     finally:
         g.close()
+
+
+def test_config2_full_size_properties():
+    """BASELINE.json config 2 at full size (mockup_only, 1024x1024, 1 000 plans x 20 viewpoints, 18 k distinct edges, 2e5 camera
+    poses) is out of the oracle's reach; size-independent properties instead: cold == warm == cold again after clearing the memo
+    (determinism of the rendering), rows follow a permutation of the plans, a prefix plan never covers more than the whole plan,
+    path length is additive, and the memo holds exactly the distinct directed edges of the population."""
+    from inspection_path_planning_b200 import cpp_binding
+    g = cpp_binding.PlanCoverageEstimator(mesh_path("mockup_only"), specs(1024))
+    try:
+        rng = np.random.default_rng(20261019)
+        N = g.getNumberOfBoxes()
+        plans = random_plans(rng, N, 1000, 20)
+        cold = g.evaluatePopulation(plans, True, True)
+        edges = {(p[k][0], p[k + 1][0]) for p in plans for k in range(len(p) - 1)}
+        assert g.memo_size() == len(edges)
+        warm = g.evaluatePopulation(plans, True, True)
+        assert np.array_equal(cold, warm)
+        g.clear_memo()
+        again = g.evaluatePopulation(plans, True, True)
+        assert np.array_equal(cold, again)
+        perm = rng.permutation(len(plans))
+        assert np.array_equal(g.evaluatePopulation([plans[i] for i in perm], True, True), cold[perm])
+        # prefixes: coverage is monotone, path length additive
+        pre = g.evaluatePopulation([p[:10] for p in plans], True, True)
+        suf = g.evaluatePopulation([p[9:] for p in plans], True, True)
+        assert np.all(1 - pre[:, 0] <= 1 - cold[:, 0] + 1e-12)
+        np.testing.assert_allclose(pre[:, 2] + suf[:, 2], cold[:, 2], rtol=1e-12)
+        assert np.all(cold[:, 0] > 0) and np.all(cold[:, 0] < 1) and (1 - cold[:, 0]).mean() > 0.3
+        # the other kernel variant renders the same population to within the flip budget's area
+        g.visibility_variant(False)
+        g.clear_memo()
+        sub = g.evaluatePopulation(plans[:60], True, True)
+        assert np.array_equal(sub[:, 1:], cold[:60, 1:])
+        assert np.abs(sub[:, 0] - cold[:60, 0]).max() < 5e-4 * 20
+    finally:
+        g.close()
