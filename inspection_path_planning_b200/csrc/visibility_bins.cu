@@ -355,11 +355,8 @@ void launch_leaf_table_t(const DeviceScene& sc, const CameraParams& cam, const S
                          cudaStream_t st) {
     using Sort = cub::BlockRadixSort<unsigned long long, THREADS, ITEMS, cub::NullType, kSortRadixBits>;
     const size_t smem = std::max(sizeof(typename Sort::TempStorage), (size_t)THREADS * ITEMS * sizeof(unsigned long long));
-    static bool configured = false;
-    if (!configured) {
-        IPP_CUDA_CHECK(cudaFuncSetAttribute(k_leaf_table<THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the current device's context, and a process may own evaluators on several devices
+    IPP_CUDA_CHECK(cudaFuncSetAttribute(k_leaf_table<THREADS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_leaf_table<THREADS, ITEMS><<<nSnaps, THREADS, smem, st>>>(sc, cam, d_snaps, b.stride, b.table, b.tableCount, b.tileMask, b.superMask,
                                                                b.nSuper);
 }
