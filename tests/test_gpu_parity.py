@@ -527,3 +527,48 @@ def test_config2_full_size_properties():
         assert np.abs(sub[:, 0] - cold[:60, 0]).max() < 5e-4 * 20
     finally:
         g.close()
+
+
+def test_mesh_ingest_stl_and_obj_match_the_oracle_loader(oracle_mod, tmp_path):
+    """osgDB::readNodeFile replacement (csrc/mesh_io.cpp): binary STL, ASCII STL and quad OBJ (Y-up -> Z-up, fan split) give the
+    same file-order triangles as the oracle's loader -- compared through the per-triangle Heron areas and the bounding box."""
+    from inspection_path_planning_b200 import cpp_binding, synth_meshes
+    tris = synth_meshes.cube(side=2.0, n=3, centre=(0.5, -0.25, 1.0))
+    stl_b, stl_a, obj = str(tmp_path / "cube_b.stl"), str(tmp_path / "cube_a.stl"), str(tmp_path / "grid.obj")
+    synth_meshes.write_binary_stl(stl_b, tris)
+    with open(stl_a, "w") as f:
+        f.write("solid cube\n")
+        for t in tris:
+            f.write(" facet normal 0 0 0\n  outer loop\n")
+            for v in t:
+                f.write("   vertex %.9g %.9g %.9g\n" % tuple(v))
+            f.write("  endloop\n endfacet\n")
+        f.write("endsolid cube\n")
+    # a 3 x 3 grid of quads bent out of plane plus one pentagon, Y-up, with vt/vn style face tokens
+    gx, gy = np.meshgrid(np.arange(4.0), np.arange(4.0), indexing="ij")
+    verts = np.stack([gx.ravel(), 0.3 * np.sin(gx.ravel() + gy.ravel()) + 2.0, gy.ravel()], axis=1)
+    with open(obj, "w") as f:
+        f.write("# test\no grid\n")
+        for v in verts:
+            f.write("v %.6f %.6f %.6f\n" % tuple(v))
+        for i in range(3):
+            for j in range(3):
+                a, b, c, d = i * 4 + j, (i + 1) * 4 + j, (i + 1) * 4 + j + 1, i * 4 + j + 1
+                f.write("f %d/1/1 %d/1/1 %d/1/1 %d/1/1\n" % (a + 1, b + 1, c + 1, d + 1))
+        f.write("f 1 5 9 13 14\nf -1 -2 -6\n")
+    sp = specs(32)
+    for path, want_t in ((stl_b, len(tris)), (stl_a, len(tris)), (obj, 9 * 2 + 3 + 1)):
+        # postProcessing=True: no seed plans are generated (a thin sheet has no contour to circle), only the ingest is exercised
+        g = cpp_binding.PlanCoverageEstimator(path, sp, True)
+        o = oracle_mod.Oracle(path, sp, post_processing=True)
+        try:
+            assert g.T == o.T == want_t
+            assert np.array_equal(g.areas(), o.areas())
+            assert np.array_equal(g.scene_info()[1], o.scene_info()[1])
+            assert g.getNumberOfBoxes() == o.getNumberOfBoxes()
+        finally:
+            g.close()
+    with pytest.raises(ValueError):
+        cpp_binding.PlanCoverageEstimator(str(tmp_path / "missing.stl"), sp)
+    with pytest.raises(ValueError):
+        cpp_binding.PlanCoverageEstimator(__file__, sp)
