@@ -21,6 +21,10 @@ constexpr int kNoId = 0x7fffffff;
 constexpr float kDepthTie = 1.0f + 1.0f / 65536.0f;
 constexpr int kTriWords = 16;  // floats per staged triangle
 constexpr int kPending = 32;   // triangles staged together (one per lane)
+#ifndef IPP_BLOCKS_PER_STEP
+#define IPP_BLOCKS_PER_STEP 2
+#endif
+constexpr int kBlocksPerStep = IPP_BLOCKS_PER_STEP;  // 8x4 blocks one step of the raster loop tests
 
 // a*b - c*d and a.b with a fixed rounding sequence.  Explicit intrinsics: the compiler may neither contract nor reassociate them, so
 // the same inputs give the same bits everywhere and negated inputs give exactly negated results -- the property the shared-edge
@@ -148,37 +152,39 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
         const float cb = __fmaf_rn(ebs, ebs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(ebu, ebu >= 0.f ? g.bYmax : g.bYmin, ebf));
         const float cc = __fmaf_rn(ecs, ecs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(ecu, ecu >= 0.f ? g.bYmax : g.bYmin, ecf));
         unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && zloTri <= bz);
-        // two blocks per step: their tests are independent (different pixels), which hides the latency of one behind the other
+        // kBlocksPerStep blocks per step: their tests are independent (different pixels), which hides the latency of one behind
+        // the others
         while (todo) {
-            const int blk0 = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const bool two = todo != 0u;
-            const int blk1 = two ? __ffs(todo) - 1 : blk0;
-            todo &= todo - 1;  // no-op on 0
-            const float X0 = __fmaf_rn((float)(blk0 & 3), g.kx8, g.Xl), Y0 = __fmaf_rn((float)(blk0 >> 2), g.ky4, g.Yl);
-            const float X1 = __fmaf_rn((float)(blk1 & 3), g.kx8, g.Xl), Y1 = __fmaf_rn((float)(blk1 >> 2), g.ky4, g.Yl);
-            const float eu0 = __fmaf_rn(eas, X0, __fmaf_rn(eau, Y0, eaf)), ev0 = __fmaf_rn(ebs, X0, __fmaf_rn(ebu, Y0, ebf)),
-                        ew0 = __fmaf_rn(ecs, X0, __fmaf_rn(ecu, Y0, ecf));
-            const float eu1 = __fmaf_rn(eas, X1, __fmaf_rn(eau, Y1, eaf)), ev1 = __fmaf_rn(ebs, X1, __fmaf_rn(ebu, Y1, ebf)),
-                        ew1 = __fmaf_rn(ecs, X1, __fmaf_rn(ecu, Y1, ecf));
-            const bool in0 = fminf(fminf(eu0, ev0), ew0) >= 0.f;         // the ray crosses the triangle
-            const bool in1 = two && fminf(fminf(eu1, ev1), ew1) >= 0.f;
-            const float t0 = vol * rcp_approx(gs * X0 + (gu * Y0 + gf));  // det == 0: inf / NaN fails the range test
-            const float t1 = vol * rcp_approx(gs * X1 + (gu * Y1 + gf));
-            const int idx0 = blk0 * 32 + lane, idx1 = blk1 * 32 + lane;
-            const float ht0 = St[idx0], ht1 = St[idx1];
-            // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
-            if (in0 && t0 >= zNear && t0 <= zFar && t0 <= ht0 * kDepthTie) {
-                const int hid = Sid[idx0];
-                Sid[idx0] = (t0 * kDepthTie < ht0) ? id : min(hid, id);  // clearly nearer: replace; inside the band: lowest id
-                St[idx0] = fminf(ht0, t0);
-                dirty = true;
+            int blk[kBlocksPerStep];
+            bool use[kBlocksPerStep];
+#pragma unroll
+            for (int u = 0; u < kBlocksPerStep; ++u) {
+                use[u] = todo != 0u;
+                blk[u] = use[u] ? __ffs(todo) - 1 : 0;
+                todo &= todo - 1;  // no-op on 0
             }
-            if (in1 && t1 >= zNear && t1 <= zFar && t1 <= ht1 * kDepthTie) {
-                const int hid = Sid[idx1];
-                Sid[idx1] = (t1 * kDepthTie < ht1) ? id : min(hid, id);
-                St[idx1] = fminf(ht1, t1);
-                dirty = true;
+            float tt[kBlocksPerStep], ht[kBlocksPerStep];
+            bool in[kBlocksPerStep];
+            int idx[kBlocksPerStep];
+#pragma unroll
+            for (int u = 0; u < kBlocksPerStep; ++u) {
+                const float X = __fmaf_rn((float)(blk[u] & 3), g.kx8, g.Xl), Y = __fmaf_rn((float)(blk[u] >> 2), g.ky4, g.Yl);
+                const float eu = __fmaf_rn(eas, X, __fmaf_rn(eau, Y, eaf)), ev = __fmaf_rn(ebs, X, __fmaf_rn(ebu, Y, ebf)),
+                            ew = __fmaf_rn(ecs, X, __fmaf_rn(ecu, Y, ecf));
+                in[u] = use[u] && fminf(fminf(eu, ev), ew) >= 0.f;  // the ray crosses the triangle
+                tt[u] = vol * rcp_approx(gs * X + (gu * Y + gf));    // det == 0: inf / NaN fails the range test
+                idx[u] = blk[u] * 32 + lane;
+                ht[u] = St[idx[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < kBlocksPerStep; ++u) {
+                // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
+                if (in[u] && tt[u] >= zNear && tt[u] <= zFar && tt[u] <= ht[u] * kDepthTie) {
+                    const int hid = Sid[idx[u]];
+                    Sid[idx[u]] = (tt[u] * kDepthTie < ht[u]) ? id : min(hid, id);  // clearly nearer: replace; inside the band: lowest id
+                    St[idx[u]] = fminf(ht[u], tt[u]);
+                    dirty = true;
+                }
             }
         }
     }
