@@ -43,7 +43,7 @@ static_assert(kLeafMax <= 8, "queue entries hold 3 bits of triangle index");
 // leaf table
 // ---------------------------------------------------------------------------------------------------------------------
 template <int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) k_leaf_table(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps, int stride,
+__global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_table(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps, int stride,
                                                         unsigned long long* __restrict__ table, int* __restrict__ tableCount,
                                                         uint32_t* __restrict__ tileMask, unsigned long long* __restrict__ superMask,
                                                         int* __restrict__ nSuper) {
