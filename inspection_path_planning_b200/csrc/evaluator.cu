@@ -479,6 +479,7 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
     bind();
     if (d_angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
     if (pop <= 0) return;
+    requireQuickHeading();
     if (pop > activeCap_) {
         cudaFree(d_active_);
         activeCap_ = pop + pop / 4 + 16;
@@ -620,6 +621,7 @@ void Evaluator::interpretPlan(const double* genes, int n, int width, double* pos
     *nPos = 0;
     *nDirs = 0;
     if (n == 0) return;
+    requireQuickHeading();
     D3 center = d3(sceneCenter_[0], sceneCenter_[1], sceneCenter_[2]);
     std::vector<D3> p;
     if (hasStart_) p.push_back(d3(start_[0], start_[1], start_[2]));
@@ -644,8 +646,18 @@ void Evaluator::interpretPlan(const double* genes, int n, int width, double* pos
 // ---------------------------------------------------------------------------------------------
 // test hooks
 // ---------------------------------------------------------------------------------------------
+// postProcessing = true switches the reference to calculateViewingDirectionTowardsPrimitives (OsgHelpers.cpp:451-489): both
+// candidate headings of every edge are rendered and the one that covers more wins.  That mode is not built;
+// answering with the quick heading instead would be a silent change of results, so every heading-dependent call refuses.
+void Evaluator::requireQuickHeading() const {
+    if (postProcessing_)
+        throw std::logic_error("libipp: postProcessing = true (heading search towards the primitives) is not implemented; construct the "
+                               "evaluator with postProcessing = false");
+}
+
 void Evaluator::edgeBitmap(int prev, int curr, double angle, uint32_t* out) {
     bind();
+    requireQuickHeading();
     if (prev == -1) {
         if (!hasStart_) throw std::invalid_argument("libipp: no start location");
         prev = N_;

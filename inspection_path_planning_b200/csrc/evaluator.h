@@ -77,6 +77,7 @@ class Evaluator {
     void renderNewEdges(int nNew, const float* d_angles);
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
     void renderSnapshots(int nSnaps, int32_t* d_idImage);
+    void requireQuickHeading() const;
     void ensurePlanBuffers(int64_t pop, int64_t nGenes);
     void ensureSnapBuffers(int64_t nSnaps);
     int readInt(const int* d);

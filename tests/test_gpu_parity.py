@@ -572,3 +572,17 @@ def test_mesh_ingest_stl_and_obj_match_the_oracle_loader(oracle_mod, tmp_path):
         cpp_binding.PlanCoverageEstimator(str(tmp_path / "missing.stl"), sp)
     with pytest.raises(ValueError):
         cpp_binding.PlanCoverageEstimator(__file__, sp)
+
+
+def test_post_processing_mode_refuses_instead_of_answering_with_the_quick_heading():
+    from inspection_path_planning_b200 import cpp_binding
+    g = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), specs(64), True)
+    try:
+        assert g.getMaxAllowedEnergy() == -1 and g.getNumberOfBoxes() > 0
+        assert g.evaluatePlan([], True, cpp_binding.nothing) == (1.0, 0.0)  # the empty plan needs no heading
+        for call in (lambda: g.evaluatePlan([[1], [2]], True, cpp_binding.nothing), lambda: g.evaluatePopulation([[[1], [2]]], True, True),
+                     lambda: g.interpretAndExportPlan([[1], [2]])):
+            with pytest.raises(RuntimeError, match="postProcessing"):
+                call()
+    finally:
+        g.close()
