@@ -7,7 +7,15 @@
 
 The first waypoint carries a dummy orientation (the way to it is not part of the plan); every other waypoint carries the heading
 followed on the way to it, as yaw only (settings/Utilities.py:268-284).  Optional rotation about +z (degrees) is applied to
-positions and headings before the position offset, as the reference does.  The reference's sharp-turn splitting
+positions and headings before the position offset, as the reference does.
+
+Difference to the reference: its exporter builds the evaluator with postProcessing=True (evolutionary_operators/
+planEvaluatorSetup.py:13-24), i.e. every exported heading comes from the heading search towards the primitives
+(OsgHelpers.cpp:451-489: render both perpendicular directions, keep the one that covers more).  That search is not built here
+(SURVEY 8(f) N4); this exporter writes the headings the optimiser evaluated the plan with (calculateViewingDirection, flipped
+towards the scene centre), which is the same axis and may be the opposite sign on edges where the far side shows more surface.
+
+The reference's sharp-turn splitting
 (split_sharply_turning_waypoints, :37-81) calls a split_waypoint() that is defined nowhere in its tree; it is not restated.
 """
 import argparse
