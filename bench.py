@@ -225,7 +225,17 @@ def run_gpu(args):
         obj = [idbuf.tobytes()]
         dist.broadcast_object_list(obj, src=0)
         idbuf = np.frombuffer(obj[0], dtype=np.uint8).copy()
-        _lib.check(L.ipp_comm_init(h, rank, world, idbuf.ctypes.data_as(_lib.c_u8p)))
+        # NCCL prints its version banner to stdout when NCCL_DEBUG is set in the environment; stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            _lib.check(L.ipp_comm_init(h, rank, world, idbuf.ctypes.data_as(_lib.c_u8p)))
+            _lib.check(L.ipp_comm_barrier(h))  # first collective: lazy NCCL set-up (and its log lines) happens here
+            ev.sync()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
