@@ -170,8 +170,10 @@ int ipp_set_profiling(ipp_t* h, int on);
 int ipp_comm_unique_id(uint8_t* out128);
 int ipp_comm_init(ipp_t* h, int rank, int world, const uint8_t* id128);
 int ipp_comm_destroy(ipp_t* h);
-/* evaluate this rank's contiguous shard of the population and all-gather the
- * fitness rows (one ncclAllGather over NVLink) so every rank holds all pop x 4. */
+/* Every rank passes the same whole population.  The edges of the population that no rank has rendered yet are rendered once
+ * across the ranks (contiguous chunks of the sorted new keys) and their bitmap rows all-gathered, so that every rank's edge memo
+ * is complete; then this rank evaluates its contiguous shard and the fitness rows are all-gathered (ncclAllGather over NVLink):
+ * every rank holds all pop x 4.  The ranks must have evaluated the same populations before (same memo contents; checked). */
 int ipp_evaluate_population_sharded(ipp_t* h, const int32_t* ids, const float* angles, const int64_t* offsets,
                                     int64_t pop, int memoization, int disable_energy_limit, double* fitness_popx4);
 /* Device-resident form of the same step: this rank's `mine` plans (CSR on the device, offsets starting at 0) are

@@ -176,8 +176,9 @@ class PlanCoverageEstimator(object):
         return (fit, ub) if union_bitmap else fit
 
     def evaluatePopulationSharded(self, plans, memoization=True, disableEnergyLimit=False, out=None):
-        """Multi-GPU form (after comm_init): this rank evaluates its contiguous shard, one NCCL all-gather returns every
-        plan's fitness row to every rank."""
+        """Multi-GPU form (after comm_init): every rank passes the same whole population.  The edges nobody has rendered yet are
+        rendered once across the ranks and their bitmap rows exchanged (NCCL all-gather), then this rank evaluates its contiguous
+        shard and one more all-gather returns every plan's fitness row to every rank."""
         ids, offsets = plans if isinstance(plans, tuple) else pack_population(plans)
         pop = offsets.size - 1
         fit = out if out is not None else np.empty((pop, 4), dtype=np.float64)

@@ -59,6 +59,10 @@ struct Comm {
     int32_t* d_ids = nullptr;
     int64_t* d_offsets = nullptr;
     int64_t idsCap = 0, offCap = 0;
+    int32_t* d_allIds = nullptr;  // whole population (shared edge rendering)
+    int64_t* d_allOffsets = nullptr;
+    int64_t allIdsCap = 0, allOffCap = 0;
+    bool shareEdges = true;
 };
 
 void comm_unique_id(uint8_t out128[128]) {
@@ -77,6 +81,7 @@ Comm* comm_create(int rank, int world, const uint8_t id128[128], cudaStream_t st
     memcpy(&id, id128, 128);
     nccl_check(api().CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
     IPP_CUDA_CHECK(cudaMalloc(&c->d_small, 64 * sizeof(double)));
+    if (const char* e = getenv("IPP_SHARE_EDGES")) c->shareEdges = atoi(e) != 0;
     return c;
 }
 void comm_destroy(Comm* c) {
@@ -86,6 +91,8 @@ void comm_destroy(Comm* c) {
     cudaFree(c->d_gather);
     cudaFree(c->d_ids);
     cudaFree(c->d_offsets);
+    cudaFree(c->d_allIds);
+    cudaFree(c->d_allOffsets);
     delete c;
 }
 int comm_rank(const Comm* c) { return c->rank; }
@@ -98,6 +105,20 @@ void comm_allreduce(Comm* c, double* inout, int n, int op, cudaStream_t st) {
     IPP_CUDA_CHECK(cudaMemcpyAsync(inout, c->d_small, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     IPP_CUDA_CHECK(cudaStreamSynchronize(st));
 }
+
+namespace {
+struct NcclCollectives : Collectives {
+    Comm* c;
+    explicit NcclCollectives(Comm* cc) : c(cc) {
+        rank = cc->rank;
+        world = cc->world;
+    }
+    void allGatherInPlace(void* d_buf, size_t bytesPerRank, cudaStream_t st) override {
+        nccl_check(api().AllGather((const char*)d_buf + (size_t)rank * bytesPerRank, d_buf, bytesPerRank, ncclChar, c->comm, st), "ncclAllGather (rows)");
+    }
+    void allReduceMax(double* inout, int n, cudaStream_t st) override { comm_allreduce(c, inout, n, 1, st); }
+};
+}  // namespace
 
 void comm_eval_device_and_allgather(Evaluator& ev, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t mine,
                                     int64_t nGenes, int64_t per, bool memo, bool noLimit, double* d_gather) {
@@ -134,6 +155,25 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
         cudaFree(c->d_offsets);
         c->offCap = mine + mine / 4 + 16;
         IPP_CUDA_CHECK(cudaMalloc(&c->d_offsets, (size_t)c->offCap * sizeof(int64_t)));
+    }
+    // The edges of the WHOLE population are rendered once across the ranks and exchanged (second exchange step of this path: the
+    // fresh bitmap rows), so that a rank does not render an edge its shard shares with another rank's shard.
+    if (c->world > 1 && pop > 0 && c->shareEdges) {
+        const int64_t allGenes = offsets[pop];
+        if (allGenes + 1 > c->allIdsCap) {
+            cudaFree(c->d_allIds);
+            c->allIdsCap = allGenes + allGenes / 4 + 16;
+            IPP_CUDA_CHECK(cudaMalloc(&c->d_allIds, (size_t)c->allIdsCap * sizeof(int32_t)));
+        }
+        if (pop + 2 > c->allOffCap) {
+            cudaFree(c->d_allOffsets);
+            c->allOffCap = pop + pop / 4 + 16;
+            IPP_CUDA_CHECK(cudaMalloc(&c->d_allOffsets, (size_t)c->allOffCap * sizeof(int64_t)));
+        }
+        IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_allIds, ids, (size_t)allGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_allOffsets, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        NcclCollectives cx(c);
+        ev.renderEdgesShared(c->d_allIds, c->d_allOffsets, pop, noLimit, cx);
     }
     std::vector<int64_t> off((size_t)mine + 1);
     for (int64_t i = 0; i <= mine; ++i) off[i] = offsets[lo + i] - g0;

@@ -216,6 +216,7 @@ Evaluator::~Evaluator() {
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
     cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
     cudaFree(bins_.scratch); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
+    cudaFree(d_sortedKeys_); cudaFree(d_sortTmp_); cudaFree(d_exchange_); cudaFree(d_activeShared_); cudaFree(d_fitShared_);
     cudaFree(d_ids_); cudaFree(d_offsets_); cudaFree(d_fitness_); cudaFree(d_active_); cudaFree(d_union_);
     cudaFree(d_flushBuf_);
     for (auto& e : pendingEv_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -455,22 +456,122 @@ void Evaluator::renderBatch(const int* d_keys, const float* d_angles, int n, con
     nEdgesRendered_ += n;
 }
 
-void Evaluator::renderNewEdges(int nNew, const float* d_angles) {
+void Evaluator::renderNewEdges(int nNew, const float* d_angles) { renderKeys(d_newKeys_, nNew, d_angles); }
+
+// K3 + K4 + pack for n claimed keys (rowmap == -2), in batches that respect the flag rows and the pose budget
+void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles) {
+    if (nNew <= 0) return;
     // camera poses per edge, so that a batch respects both the flag rows and the pose budget (leaf tables, int32 work offsets)
     std::vector<int> perEdge(nNew);
-    launch_count_snapshots(d_newKeys_, nNew, d_pos_, N_, cam_, d_countsAll_, stream_);
+    launch_count_snapshots(d_keys, nNew, d_pos_, N_, cam_, d_countsAll_, stream_);
     IPP_CUDA_CHECK(cudaMemcpyAsync(perEdge.data(), d_countsAll_, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
     sync();
     nLaunches_++;
     for (int b0 = 0, n = 0; b0 < nNew; b0 += n) {
         int64_t snaps = 0;
         for (n = 0; b0 + n < nNew && n < batchCap_ && (n == 0 || snaps + perEdge[b0 + n] <= maxSnapsPerBatch_); ++n) snaps += perEdge[b0 + n];
-        launch_assign_rows(d_newKeys_ + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
-        renderBatch(d_newKeys_ + b0, d_angles ? d_angles + b0 : nullptr, n, d_rowOfSlot_);
-        launch_publish_rows(d_newKeys_ + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
+        launch_assign_rows(d_keys + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
+        renderBatch(d_keys + b0, d_angles ? d_angles + b0 : nullptr, n, d_rowOfSlot_);
+        launch_publish_rows(d_keys + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
         nLaunches_ += 2;
     }
     liveRows_ += nNew;
+}
+
+int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx) {
+    bind();
+    if (pop <= 0) return 0;
+    requireQuickHeading();
+    if (pop > sharedCap_) {
+        cudaFree(d_activeShared_);
+        cudaFree(d_fitShared_);
+        sharedCap_ = pop + pop / 4 + 16;
+        d_activeShared_ = dalloc<uint8_t>(sharedCap_);
+        d_fitShared_ = dalloc<double>(sharedCap_ * 4);
+    }
+    // 1. collision flags of the whole population (replicated: a millisecond per 20 k edges), energy gate, then the edges
+    //    whose bitmap nobody has yet
+    PlanMarkArgs mk;
+    mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
+    mk.active = nullptr; mk.coll = d_coll_; mk.rowmap = nullptr; mk.used = nullptr; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
+    mk.errFlag = d_scalars_ + 3;
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 3, 0, sizeof(int), stream_));
+    launch_mark_collisions(mk, stream_);
+    nLaunches_++;
+    readScalars();
+    if (h_scalars_[3]) throw std::out_of_range("libipp: box id out of range");
+    if (h_scalars_[0] > 0) {
+        launch_collide_keys(scene_, d_newKeys_, h_scalars_[0], d_pos_, N_, d_coll_, stream_);
+        nLaunches_++;
+        nCollisionQueries_ += h_scalars_[0];
+    }
+    PlanEnergyArgs en;
+    en.ids = d_ids; en.offsets = d_offsets; en.pop = pop; en.N = N_; en.hasStart = hasStart_; en.loops = loops_;
+    en.pos = d_pos_; en.coll = d_coll_; en.collisionPenalty = collisionPenalty_; en.maxEnergy = maxAllowedEnergy_;
+    en.disableLimit = noLimit; en.fitness = d_fitShared_; en.active = d_activeShared_;
+    launch_energy(en, stream_);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+    mk.active = d_activeShared_; mk.coll = nullptr; mk.rowmap = d_rowmap_;
+    launch_mark_rows(mk, stream_);
+    nLaunches_ += 2;
+    readScalars();
+    const int nNew = h_scalars_[0], freeRows = h_scalars_[1];
+    // 2. every rank must have found the same set (same population, same memo contents)
+    //    (the cache-full condition is agreed on too: no rank may leave the others waiting in a collective)
+    double agree[3] = {(double)nNew, -(double)nNew, nNew > freeRows ? 1.0 : 0.0};
+    cx.allReduceMax(agree, 3, stream_);
+    if (agree[0] != (double)nNew || agree[1] != -(double)nNew)
+        throw std::runtime_error("libipp: the ranks disagree on the new edges of the population (different populations or memo contents)");
+    if (nNew == 0) return 0;
+    if (agree[2] != 0.0)
+        throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
+                                 " free rows); call updateMemoisedEdges or evaluate a smaller batch");
+    // 3. the same order everywhere: ascending keys
+    if (!d_sortedKeys_) d_sortedKeys_ = dalloc<int>(nKeys_);
+    size_t need = sort_tmp_bytes(nNew);
+    if (need > sortTmpBytes_) {
+        cudaFree(d_sortTmp_);
+        sortTmpBytes_ = need * 2;
+        IPP_CUDA_CHECK(cudaMalloc(&d_sortTmp_, sortTmpBytes_));
+    }
+    sort_keys_i32(d_newKeys_, d_sortedKeys_, nNew, d_sortTmp_, sortTmpBytes_, stream_);
+    nLaunches_++;
+    // 4. this rank renders its contiguous chunk
+    const int G = cx.world, r = cx.rank;
+    const int chunk = (nNew + G - 1) / G;
+    const int lo = std::min(nNew, r * chunk), hi = std::min(nNew, lo + chunk);
+    renderKeys(d_sortedKeys_ + lo, hi - lo, nullptr);
+    // 5. exchange the fresh rows slab by slab: pack -> in-place all-gather -> rows for the other ranks' keys -> unpack
+    const int64_t rowBytes = rowWords_ * 4;
+    const int64_t slabBudget = (int64_t)1 << 30;
+    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(chunk, batchCap_), slabBudget / (rowBytes * G)));
+    const size_t needWords = (size_t)G * B * rowWords_;
+    if (needWords > exchangeWords_) {
+        cudaFree(d_exchange_);
+        exchangeWords_ = needWords;
+        d_exchange_ = dalloc<uint32_t>(exchangeWords_);
+    }
+    for (int s0 = 0; s0 < chunk; s0 += B) {
+        const int myN = std::max(0, std::min(B, hi - (lo + s0)));
+        launch_rows_gather(d_sortedKeys_ + lo + s0, myN, d_rowmap_, d_rows_, rowWords_, d_exchange_ + (size_t)r * B * rowWords_, stream_);
+        cx.allGatherInPlace(d_exchange_, (size_t)B * rowBytes, stream_);
+        nLaunches_ += 2;
+        for (int q = 0; q < G; ++q) {
+            if (q == r) continue;
+            const int qlo = std::min(nNew, q * chunk), qhi = std::min(nNew, qlo + chunk);
+            const int qN = std::max(0, std::min(B, qhi - (qlo + s0)));
+            if (qN == 0) continue;
+            const int* keys = d_sortedKeys_ + qlo + s0;
+            launch_assign_rows(keys, qN, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
+            launch_rows_scatter(d_exchange_ + (size_t)q * B * rowWords_, d_rowOfSlot_, qN, d_rows_, rowWords_, stream_);
+            launch_publish_rows(keys, d_rowOfSlot_, qN, d_rowmap_, stream_);
+            nLaunches_ += 3;
+            liveRows_ += qN;
+        }
+    }
+    sync();
+    return hi - lo;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,6 +15,15 @@ namespace ipp {
 
 struct Comm;  // comm.cpp
 
+// What renderEdgesShared needs from the communicator (implemented on NCCL in comm.cu).
+struct Collectives {
+    int rank = 0, world = 1;
+    virtual ~Collectives() {}
+    // in place: every rank contributes bytesPerRank bytes at d_buf + rank * bytesPerRank and receives all slots
+    virtual void allGatherInPlace(void* d_buf, size_t bytesPerRank, cudaStream_t st) = 0;
+    virtual void allReduceMax(double* inout, int n, cudaStream_t st) = 0;
+};
+
 enum KernelGroup { KG_REDUCE = 0, KG_VISIBILITY = 1, KG_COLLISION = 2, KG_PACK = 3, KG_PLAN = 4, KG_TABLE = 5, KG_COUNT = 6 };
 
 class Evaluator {
@@ -33,6 +42,10 @@ class Evaluator {
                                 double* fitness, uint32_t* unionBitmap);
     void evaluatePopulationDevice(const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t pop, int64_t nGenes,
                                   bool memo, bool noLimit, double* d_fitness, uint32_t* unionBitmapHost);
+    // Multi-GPU: the edges the WHOLE population needs are rendered once across the ranks (contiguous chunks of the sorted new
+    // keys), the fresh bitmap rows are all-gathered, and every rank's memo ends up complete.  Every rank must pass the same
+    // population and hold the same memo contents (checked).  Returns the number of edges this rank rendered itself.
+    int64_t renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx);
     int64_t updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
     int64_t memoSize() const { return liveRows_; }
     void clearMemo();
@@ -75,6 +88,7 @@ class Evaluator {
 
    private:
     void renderNewEdges(int nNew, const float* d_angles);
+    void renderKeys(const int* d_keys, int n, const float* d_angles);
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
     void renderSnapshots(int nSnaps, int32_t* d_idImage);
     void requireQuickHeading() const;
@@ -124,6 +138,15 @@ class Evaluator {
     BinBuffers bins_;
     int* d_superOffset_ = nullptr;
     int* d_countsAll_ = nullptr;  // snapshots per new edge (nKeys + 1)
+    // shared rendering across ranks
+    int* d_sortedKeys_ = nullptr;  // nKeys
+    void* d_sortTmp_ = nullptr;
+    size_t sortTmpBytes_ = 0;
+    uint32_t* d_exchange_ = nullptr;  // world x slab x rowWords
+    size_t exchangeWords_ = 0;
+    uint8_t* d_activeShared_ = nullptr;
+    double* d_fitShared_ = nullptr;
+    int64_t sharedCap_ = 0;
     int64_t maxSnapsPerBatch_ = 1 << 20;
     float* d_angleOne_ = nullptr;
 

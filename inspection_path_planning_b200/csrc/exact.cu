@@ -484,4 +484,27 @@ void launch_publish_rows(const int* d_keys, const int* d_rows, int n, int* d_row
     if (n > 0) k_publish_rows<<<(n + 255) / 256, 256, 0, st>>>(d_keys, d_rows, n, d_rowmap);
 }
 
+
+__global__ void k_rows_gather(const int* __restrict__ keys, int n, const int* __restrict__ rowmap, const uint4* __restrict__ rows,
+                              int q4, uint4* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * q4) return;
+    int k = (int)(i / q4), w = (int)(i - (long long)k * q4);
+    out[i] = rows[(size_t)rowmap[keys[k]] * q4 + w];
+}
+__global__ void k_rows_scatter(const uint4* __restrict__ in, const int* __restrict__ rowOfSlot, int n, uint4* __restrict__ rows, int q4) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)n * q4) return;
+    int k = (int)(i / q4), w = (int)(i - (long long)k * q4);
+    rows[(size_t)rowOfSlot[k] * q4 + w] = in[i];
+}
+void launch_rows_gather(const int* d_keys, int n, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_out, cudaStream_t st) {
+    long long t = (long long)n * (rowWords / 4);
+    if (t > 0) k_rows_gather<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(d_keys, n, d_rowmap, (const uint4*)d_rows, (int)(rowWords / 4), (uint4*)d_out);
+}
+void launch_rows_scatter(const uint32_t* d_in, const int* d_rowOfSlot, int n, uint32_t* d_rows, int64_t rowWords, cudaStream_t st) {
+    long long t = (long long)n * (rowWords / 4);
+    if (t > 0) k_rows_scatter<<<(unsigned)((t + 255) / 256), 256, 0, st>>>((const uint4*)d_in, d_rowOfSlot, n, (uint4*)d_rows, (int)(rowWords / 4));
+}
+
 }  // namespace ipp

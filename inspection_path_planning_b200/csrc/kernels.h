@@ -66,6 +66,9 @@ void launch_mark_rows(const PlanMarkArgs& a, cudaStream_t st);
 void launch_gc_rows(int* d_rowmap, const uint8_t* d_used, int nKeys, int* d_freeStack, int* d_freeTop, int* d_live, cudaStream_t st);
 void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, cudaStream_t st);
 void launch_publish_rows(const int* d_keys, const int* d_rows, int n, int* d_rowmap, cudaStream_t st);
+// bitmap rows of n keys <-> a contiguous staging buffer (n x rowWords), for the exchange of freshly rendered rows between ranks
+void launch_rows_gather(const int* d_keys, int n, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_out, cudaStream_t st);
+void launch_rows_scatter(const uint32_t* d_in, const int* d_rowOfSlot, int n, uint32_t* d_rows, int64_t rowWords, cudaStream_t st);
 
 // lbvh.cu
 // Builds the BVH over the non-degenerate triangles.  d_verts / d_canon: T x 9 floats (file / canonical vertex order).
@@ -106,6 +109,8 @@ void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Sna
 void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_superOffset, int nSnaps,
                             int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters,
                             cudaStream_t st);
+size_t sort_tmp_bytes(int n);
+void sort_keys_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);  // ascending, keys >= 0
 size_t scan_tmp_bytes(int n);
 void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);
 

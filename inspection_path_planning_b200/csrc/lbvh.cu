@@ -278,6 +278,14 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
     cudaFree(left); cudaFree(right); cudaFree(rlo); cudaFree(rhi); cudaFree(parentI); cudaFree(parentL); cudaFree(arrive);
 }
 
+size_t sort_tmp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n, 0, 31);
+    return std::max<size_t>(bytes, 16);
+}
+void sort_keys_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st) {
+    cub::DeviceRadixSort::SortKeys(d_tmp, tmpBytes, d_in, d_out, n, 0, 31, st);
+}
 size_t scan_tmp_bytes(int n) {
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n);
