@@ -110,7 +110,8 @@ void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, cons
                             int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters,
                             cudaStream_t st);
 size_t sort_tmp_bytes(int n);
-void sort_keys_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);  // ascending, keys >= 0
+// the same pseudo-random order of a key set on every rank (contiguous chunks of it are random samples of the set)
+void scrambled_order_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);
 size_t scan_tmp_bytes(int n);
 void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);
 

@@ -278,13 +278,32 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
     cudaFree(left); cudaFree(right); cudaFree(rlo); cudaFree(rhi); cudaFree(parentI); cudaFree(parentL); cudaFree(arrive);
 }
 
+// Deterministic pseudo-random order of a set of keys: sort by key * 0x9E3779B1 mod 2^32 (a bijection of the 32-bit integers),
+// then undo the multiplication.  Every rank that holds the same set gets the same order, and a contiguous chunk of the result is
+// a random sample of the set (neighbouring keys -- edges that leave the same viewpoint and cost alike -- end up on different ranks).
+namespace {
+__global__ void k_mul_u32(const int* __restrict__ in, unsigned* __restrict__ out, int n, unsigned m) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned)in[i] * m;
+}
+__global__ void k_mul_back(unsigned* __restrict__ io, int n, unsigned m) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) io[i] = io[i] * m;
+}
+}  // namespace
 size_t sort_tmp_bytes(int n) {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const int*)nullptr, (int*)nullptr, n, 0, 31);
-    return std::max<size_t>(bytes, 16);
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const unsigned*)nullptr, (unsigned*)nullptr, n, 0, 32);
+    return std::max<size_t>(bytes, 16) + (size_t)n * sizeof(unsigned) + 512;
 }
-void sort_keys_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st) {
-    cub::DeviceRadixSort::SortKeys(d_tmp, tmpBytes, d_in, d_out, n, 0, 31, st);
+void scrambled_order_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st) {
+    if (n <= 0) return;
+    unsigned* h = (unsigned*)d_tmp;  // the hashed keys, then the CUB workspace
+    char* work = (char*)d_tmp + (((size_t)n * sizeof(unsigned) + 255) / 256) * 256;
+    size_t workBytes = tmpBytes - (size_t)(work - (char*)d_tmp);
+    k_mul_u32<<<(n + 255) / 256, 256, 0, st>>>(d_in, h, n, 0x9E3779B1u);
+    cub::DeviceRadixSort::SortKeys(work, workBytes, h, (unsigned*)d_out, n, 0, 32, st);
+    k_mul_back<<<(n + 255) / 256, 256, 0, st>>>((unsigned*)d_out, n, 0x0E8B2F51u);
 }
 size_t scan_tmp_bytes(int n) {
     size_t bytes = 0;
