@@ -402,7 +402,9 @@ def run_gpu(args):
                                "edge_collision": col_ms / args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pop_total * VIEWPOINTS * 4 + (pop_total + 1) * 8),
-                "d2h_bytes_per_step": int(pop_total * 4 * 8), "ms_per_step": ms_e2e / args.steps, "matches_resident_path": bool(same)},
+                "d2h_bytes_per_step": int(pop_total * 4 * 8), "ms_per_step": ms_e2e / args.steps, "matches_resident_path": bool(same),
+                **({"note": "host entry point: every rank passes all ranks' plans as one population; edges two ranks' plans share are "
+                            "rendered once across the ranks and their bitmap rows all-gathered (DESIGN.md section 9)"} if world > 1 else {})},
         "gpu_launches": int(cnt["launches"]),
         "roofline": {"kernel": "k_visibility_bins" if variant == "bins" else "k_visibility", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": None, "algorithmic_bytes_per_launch": alg_bytes_launch, "us_per_launch": vis_launch_s * 1e6,
