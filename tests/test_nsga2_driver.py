@@ -162,3 +162,21 @@ def test_plan_export_yaml_follows_the_rock_format(sphere_run):
     dy = (rot[1]["orientation"]["y"] - base[1]["orientation"]["y"] - math.pi / 2 + math.pi) % (2 * math.pi) - math.pi
     assert abs(dy) < 1e-9
     assert pe.plan_to_waypoints(ev, []) == []
+
+
+def test_circling_plan_generator_stores_the_seed_plans_with_their_fitness(oracle_mod, tmp_path):
+    from inspection_path_planning_b200 import circling_plan_generator as cg
+    sp = list(oc.Parameters.SENSOR_PARAMETERS)
+    sp[3] = 64
+    params = oc.Parameters(SENSOR_PARAMETERS=sp)
+    ev = oracle_mod.Oracle(mesh_path("sphere"), sp)
+    inds = cg.generate(ev, params, "sphere.obj", str(tmp_path))
+    plans = ev.getSimplePlans()
+    assert len(inds) == len(plans) > 0
+    # the first complete plan defines the energy limit (PlanEnergyEvaluator.cpp:40-46)
+    assert inds[0].fitness[1] == pytest.approx(ev.getMaxAllowedEnergy(), rel=1e-12)
+    for ind, p in zip(inds, plans):
+        assert [g[0] for g in ind] == [int(g[0]) for g in p]
+        assert tuple(ev.evaluatePlan(list(ind), False, 3, False)) == pytest.approx(ind.fitness)
+    d = oc.load_dumped_population(str(tmp_path / "populations" / "circling_plans.yml"))
+    assert len(d["population"]) == len(inds) and d["pareto_front"] is None and d["scene"] == "sphere.obj"
