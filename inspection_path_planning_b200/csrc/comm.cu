@@ -158,7 +158,8 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
     }
     // The edges of the WHOLE population are rendered once across the ranks and exchanged (second exchange step of this path: the
     // fresh bitmap rows), so that a rank does not render an edge its shard shares with another rank's shard.
-    if (c->world > 1 && pop > 0 && c->shareEdges) {
+    // (memoization == false keeps the reference's meaning -- nothing rendered for this call is remembered -- and renders per shard)
+    if (c->world > 1 && pop > 0 && c->shareEdges && memo) {
         const int64_t allGenes = offsets[pop];
         if (allGenes + 1 > c->allIdsCap) {
             cudaFree(c->d_allIds);
