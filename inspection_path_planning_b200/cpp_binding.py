@@ -44,6 +44,14 @@ def _dp(a):
     return a.ctypes.data_as(_lib.c_f64p)
 
 
+def _gene_id(g):
+    """[id] or [id, angleOffset] (SIMPLIFIED_VIEW_ANGLE = False individuals, individuals.py:19-22): a zero offset is the
+    straight-ahead heading and evaluates like [id]; a non-zero offset is not supported by the evaluation path."""
+    if len(g) == 1 or (len(g) == 2 and float(g[1]) == 0.0):
+        return g[0]
+    raise NotImplementedError("[id, angle] genes with a non-zero angle offset are not supported by the evaluation path")
+
+
 def pack_population(plans):
     """list of plans -> (ids int32[nGenes], offsets int64[pop+1]).  Each gene is [id] (or a bare id).
     Gene -> id uses the reference's rounding `(size_t)(gene + 0.5)` (PlanInterpreterBoxOrder.cpp:280)."""
@@ -52,9 +60,7 @@ def pack_population(plans):
     for i, p in enumerate(plans):
         for g in p:
             if isinstance(g, (list, tuple, np.ndarray)):
-                if len(g) != 1:
-                    raise NotImplementedError("[id, angle] genes are not supported by the batched path yet")
-                g = g[0]
+                g = _gene_id(g)
             flat.append(g)
         offsets[i + 1] = len(flat)
     vals = np.asarray(flat, dtype=np.float64)
@@ -107,9 +113,7 @@ class PlanCoverageEstimator(object):
         genes = np.zeros((len(plan), 1), dtype=np.float64)
         for i, g in enumerate(plan):
             if isinstance(g, (list, tuple, np.ndarray)):
-                if len(g) != 1:
-                    raise NotImplementedError("[id, angle] genes are not supported by the batched path yet")
-                g = g[0]
+                g = _gene_id(g)
             genes[i, 0] = g
         out = np.zeros(4, dtype=np.float64)
         _lib.check(self._L.ipp_evaluate_plan(self._h, _dp(genes), genes.shape[0], 1, int(bool(memoization)), int(how_to_plot),

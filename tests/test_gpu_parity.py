@@ -586,3 +586,14 @@ def test_post_processing_mode_refuses_instead_of_answering_with_the_quick_headin
                 call()
     finally:
         g.close()
+
+
+def test_zero_angle_genes_evaluate_like_plain_ids(sphere):
+    g, o = sphere
+    from inspection_path_planning_b200 import cpp_binding as cb
+    plan = [[100], [101], [113]]
+    with_zero = [[100, 0], [101, 0.0], [113, 0]]
+    assert g.evaluatePlan(with_zero, True, cb.nothing) == g.evaluatePlan(plan, True, cb.nothing)
+    assert np.array_equal(g.evaluatePopulation([with_zero], True, False), g.evaluatePopulation([plan], True, False))
+    with pytest.raises(NotImplementedError):
+        g.evaluatePlan([[100, 0.3], [101, 0]], True, cb.nothing)
