@@ -597,3 +597,42 @@ def test_zero_angle_genes_evaluate_like_plain_ids(sphere):
     assert np.array_equal(g.evaluatePopulation([with_zero], True, False), g.evaluatePopulation([plan], True, False))
     with pytest.raises(NotImplementedError):
         g.evaluatePlan([[100, 0.3], [101, 0]], True, cb.nothing)
+
+
+def test_tiny_meshes_one_triangle_and_a_twelve_triangle_box(oracle_mod, tmp_path):
+    """BVH and leaf-table corner cases: a mesh of one triangle (root with a single leaf) and a box of 12 (fewer triangles than a
+    leaf holds twice over), both variants, postProcessing constructor (no seed plans needed)."""
+    from inspection_path_planning_b200 import cpp_binding, synth_meshes
+    one = np.array([[[-3.0, -2.0, 1.0], [3.0, -2.0, 1.5], [0.0, 3.0, 2.0]]], dtype=np.float32)
+    box = synth_meshes.cube(side=3.0, n=1, centre=(0.0, 0.0, 2.0))
+    for name, tris in (("one", one), ("box", box)):
+        path = str(tmp_path / (name + ".ippm"))
+        synth_meshes.write_ippm(path, tris)
+        sp = specs(96)
+        g = cpp_binding.PlanCoverageEstimator(path, sp, False if name == "box" else True)
+        o = oracle_mod.Oracle(path, sp, post_processing=(name != "box"))
+        try:
+            assert g.T == o.T == len(tris) and g.getNumberOfBoxes() == o.getNumberOfBoxes()
+            rng = np.random.default_rng(81)
+            c, bb = o.scene_info()
+            for _ in range(6):
+                eye = c + rng.normal(size=3) * 4.0
+                eye = eye.astype(np.float32).astype(np.float64)
+                for variant in (True, False):
+                    g.visibility_variant(variant)
+                    a, b = g.render_ids(eye, c, (0, 0, 1)), o.render_ids(eye, c, (0, 0, 1))
+                    assert (a != b).mean() < 4e-3, (name, variant)
+            if name == "box":
+                stats = dict(flips=0, edges=0, seen=0, outside=0)
+                N = o.getNumberOfBoxes()
+                for _ in range(8):
+                    prev, curr = (int(x) for x in rng.choice(N, 2, replace=False))
+                    for variant in (True, False):
+                        g.visibility_variant(variant)
+                        nflip, outside = _check_edge(g, o, prev, curr, stats)
+                        assert nflip == 0 or outside == 0
+                plans = random_plans(rng, N, 12, (2, 6))
+                g.visibility_variant(True)
+                _compare_population(g, o, plans, memo=True, no_limit=True)
+        finally:
+            g.close()
