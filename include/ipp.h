@@ -77,16 +77,17 @@ int ipp_grid(const ipp_t* h, int32_t* out);
  * Call with ids == NULL to obtain the sizes. */
 int ipp_simple_plans(ipp_t* h, int* n_plans, int* n_genes, double* ids, int32_t* offsets);
 
-/* evaluatePlan (cpp_binding.i:31).  genes: n x width doubles.  how_to_plot must
- * be IPP_PLOT_NOTHING (the GL viewers are out of scope).  out4 receives one
- * fitness row. */
+/* evaluatePlan (cpp_binding.i:31).  genes: n x width doubles, width 1 ([id]) or 2 ([id, angleOffsetRad],
+ * PlanInterpreterBoxOrder.cpp:278-299).  how_to_plot must be IPP_PLOT_NOTHING (the GL viewers are out of
+ * scope).  out4 receives one fitness row. */
 int ipp_evaluate_plan(ipp_t* h, const double* genes, int n, int width, int memoization, int how_to_plot,
                       int disable_energy_limit, double* out4);
 
 /* The one batched entry point: evaluatePlan over a whole population
  * (replaces toolbox.map(evaluate, ...) at plan_optimizer/optimize_coverage.py:141,191).
- * Host pointers; copies in and out are part of the call.  union_bitmap may be
- * NULL; otherwise it receives the OR of the seen sets of all plans that passed
+ * Host pointers; copies in and out are part of the call.  angles: NULL for [id] genes, otherwise one heading
+ * offset per gene (float, as the reference narrows it); edges with offsets are memoised under (previous id, id,
+ * offset).  union_bitmap may be NULL; otherwise it receives the OR of the seen sets of all plans that passed
  * the energy gate (W words). */
 int ipp_evaluate_population(ipp_t* h, const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop,
                             int memoization, int disable_energy_limit, double* fitness_popx4, uint32_t* union_bitmap);

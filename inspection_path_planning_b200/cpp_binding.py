@@ -44,29 +44,40 @@ def _dp(a):
     return a.ctypes.data_as(_lib.c_f64p)
 
 
-def _gene_id(g):
-    """[id] or [id, angleOffset] (SIMPLIFIED_VIEW_ANGLE = False individuals, individuals.py:19-22): a zero offset is the
-    straight-ahead heading and evaluates like [id]; a non-zero offset is not supported by the evaluation path."""
-    if len(g) == 1 or (len(g) == 2 and float(g[1]) == 0.0):
-        return g[0]
-    raise NotImplementedError("[id, angle] genes with a non-zero angle offset are not supported by the evaluation path")
-
-
-def pack_population(plans):
-    """list of plans -> (ids int32[nGenes], offsets int64[pop+1]).  Each gene is [id] (or a bare id).
+def pack_population(plans, with_angles=False):
+    """list of plans -> (ids int32[nGenes], offsets int64[pop+1]) or, with_angles=True, (ids, angles float32[nGenes] | None, offsets).
+    A gene is [id], a bare id, or [id, angleOffset] (SIMPLIFIED_VIEW_ANGLE = False individuals, individuals.py:19-22); angles is
+    None when every offset is zero -- the straight-ahead heading evaluates like [id] and shares its memo.
     Gene -> id uses the reference's rounding `(size_t)(gene + 0.5)` (PlanInterpreterBoxOrder.cpp:280)."""
     offsets = np.zeros(len(plans) + 1, dtype=np.int64)
-    flat = []
+    flat, ang = [], []
     for i, p in enumerate(plans):
         for g in p:
+            a = 0.0
             if isinstance(g, (list, tuple, np.ndarray)):
-                g = _gene_id(g)
+                if len(g) == 2:
+                    a = float(g[1])
+                elif len(g) != 1:
+                    raise ValueError("a gene is [id] or [id, angleOffset]")
+                g = g[0]
             flat.append(g)
+            ang.append(a)
         offsets[i + 1] = len(flat)
     vals = np.asarray(flat, dtype=np.float64)
     ids = np.trunc(vals + 0.5)
     ids[vals + 0.5 < 0] = 0.0  # a negative gene (the -1 cells of the seed plans) truncates to 0 like the reference
-    return np.ascontiguousarray(ids.astype(np.int32)), offsets
+    ids = np.ascontiguousarray(ids.astype(np.int32))
+    if not with_angles:
+        if any(a != 0.0 for a in ang):
+            raise NotImplementedError("[id, angle] genes with a non-zero offset need the host-pointer evaluation calls (evaluatePlan, "
+                                      "evaluatePopulation, updateMemoisedEdges)")
+        return ids, offsets
+    angles = np.ascontiguousarray(np.asarray(ang, dtype=np.float32)) if any(a != 0.0 for a in ang) else None
+    return ids, angles, offsets
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(_lib.c_f32p)
 
 
 class PlanCoverageEstimator(object):
@@ -109,14 +120,21 @@ class PlanCoverageEstimator(object):
 
     # ---- the reference's methods ----
     def evaluatePlan(self, plan, memoization, how_to_plot, disableEnergyLimit=False):
-        """-> (coverageScore, energy); cpp_binding.i:31."""
-        genes = np.zeros((len(plan), 1), dtype=np.float64)
+        """-> (coverageScore, energy); cpp_binding.i:31.  Genes are [id] or [id, angleOffsetRad]."""
+        width = 1
+        for g in plan:
+            if isinstance(g, (list, tuple, np.ndarray)) and len(g) == 2 and float(g[1]) != 0.0:
+                width = 2
+        genes = np.zeros((len(plan), width), dtype=np.float64)
         for i, g in enumerate(plan):
             if isinstance(g, (list, tuple, np.ndarray)):
-                g = _gene_id(g)
-            genes[i, 0] = g
+                if len(g) not in (1, 2):
+                    raise ValueError("a gene is [id] or [id, angleOffset]")
+                genes[i, :min(width, len(g))] = g[:width]
+            else:
+                genes[i, 0] = g
         out = np.zeros(4, dtype=np.float64)
-        _lib.check(self._L.ipp_evaluate_plan(self._h, _dp(genes), genes.shape[0], 1, int(bool(memoization)), int(how_to_plot),
+        _lib.check(self._L.ipp_evaluate_plan(self._h, _dp(genes), genes.shape[0], width, int(bool(memoization)), int(how_to_plot),
                                              int(bool(disableEnergyLimit)), _dp(out)))
         return (float(out[0]), float(out[1]))
 
@@ -124,9 +142,12 @@ class PlanCoverageEstimator(object):
         return int(self._L.ipp_num_boxes(self._h))
 
     def updateMemoisedEdges(self, allSolutions):
-        ids, offsets = allSolutions if isinstance(allSolutions, tuple) else pack_population(allSolutions)
+        if isinstance(allSolutions, tuple):
+            ids, angles, offsets = (allSolutions[0], None, allSolutions[1]) if len(allSolutions) == 2 else allSolutions
+        else:
+            ids, angles, offsets = pack_population(allSolutions, with_angles=True)
         rem = C.c_int64()
-        _lib.check(self._L.ipp_update_memoised_edges(self._h, ids.ctypes.data_as(_lib.c_i32p), None, offsets.ctypes.data_as(_lib.c_i64p),
+        _lib.check(self._L.ipp_update_memoised_edges(self._h, ids.ctypes.data_as(_lib.c_i32p), _fp(angles), offsets.ctypes.data_as(_lib.c_i64p),
                                                      offsets.size - 1, C.byref(rem)))
         return int(rem.value)
 
@@ -165,16 +186,19 @@ class PlanCoverageEstimator(object):
 
     # ---- the batched entry point ----
     def evaluatePopulation(self, plans, memoization=True, disableEnergyLimit=False, union_bitmap=False, out=None):
-        """Evaluates a whole population in one call.  `plans` is a list of plans or a packed (ids int32, offsets int64)
-        pair.  Returns float64 [pop, 4]: columns 0-1 are evaluatePlan's (coverageScore, energy), 2 = path length,
+        """Evaluates a whole population in one call.  `plans` is a list of plans ([id] or [id, angleOffset] genes) or a packed
+        (ids int32, offsets int64) pair / (ids, angles float32, offsets) triple.  Returns float64 [pop, 4]: columns 0-1 are evaluatePlan's (coverageScore, energy), 2 = path length,
         3 = number of colliding edges.  With union_bitmap=True also returns the OR of the seen sets (uint32 words)."""
-        ids, offsets = plans if isinstance(plans, tuple) else pack_population(plans)
+        if isinstance(plans, tuple):
+            ids, angles, offsets = (plans[0], None, plans[1]) if len(plans) == 2 else plans
+        else:
+            ids, angles, offsets = pack_population(plans, with_angles=True)
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         pop = offsets.size - 1
         fit = out if out is not None else np.empty((pop, 4), dtype=np.float64)
         ub = np.zeros(self.W32, dtype=np.uint32) if union_bitmap else None
-        _lib.check(self._L.ipp_evaluate_population(self._h, ids.ctypes.data_as(_lib.c_i32p), None, offsets.ctypes.data_as(_lib.c_i64p), pop,
+        _lib.check(self._L.ipp_evaluate_population(self._h, ids.ctypes.data_as(_lib.c_i32p), _fp(angles), offsets.ctypes.data_as(_lib.c_i64p), pop,
                                                    int(bool(memoization)), int(bool(disableEnergyLimit)), _dp(fit),
                                                    None if ub is None else ub.ctypes.data_as(_lib.c_u32p)))
         return (fit, ub) if union_bitmap else fit

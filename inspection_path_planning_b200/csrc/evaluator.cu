@@ -216,6 +216,7 @@ Evaluator::~Evaluator() {
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
     cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
     cudaFree(bins_.scratch); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
+    cudaFree(d_angleBuf_); cudaFree(d_edgeRows_); cudaFree(d_edgeOffsets_); cudaFree(d_rowList_);
     cudaFree(d_sortedKeys_); cudaFree(d_sortTmp_); cudaFree(d_exchange_); cudaFree(d_activeShared_); cudaFree(d_fitShared_);
     cudaFree(d_ids_); cudaFree(d_offsets_); cudaFree(d_fitness_); cudaFree(d_active_); cudaFree(d_union_);
     cudaFree(d_flushBuf_);
@@ -432,6 +433,7 @@ void Evaluator::clearMemo() {
     sync();
     nLaunches_ += 3;
     liveRows_ = 0;
+    angleMemo_.clear();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,8 +460,9 @@ void Evaluator::renderBatch(const int* d_keys, const float* d_angles, int n, con
 
 void Evaluator::renderNewEdges(int nNew, const float* d_angles) { renderKeys(d_newKeys_, nNew, d_angles); }
 
-// K3 + K4 + pack for n claimed keys (rowmap == -2), in batches that respect the flag rows and the pose budget
-void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles) {
+// K3 + K4 + pack for n claimed keys, in batches that respect the flag rows and the pose budget.  publish: the rows become the
+// memo entries of the keys (rowmap); otherwise they are only handed back through rowsOut ([id, angle] genes keep their own memo).
+void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles, bool publish, std::vector<int>* rowsOut) {
     if (nNew <= 0) return;
     // camera poses per edge, so that a batch respects both the flag rows and the pose budget (leaf tables, int32 work offsets)
     std::vector<int> perEdge(nNew);
@@ -467,15 +470,20 @@ void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles) {
     IPP_CUDA_CHECK(cudaMemcpyAsync(perEdge.data(), d_countsAll_, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
     sync();
     nLaunches_++;
+    if (rowsOut) rowsOut->resize(nNew);
     for (int b0 = 0, n = 0; b0 < nNew; b0 += n) {
         int64_t snaps = 0;
         for (n = 0; b0 + n < nNew && n < batchCap_ && (n == 0 || snaps + perEdge[b0 + n] <= maxSnapsPerBatch_); ++n) snaps += perEdge[b0 + n];
         launch_assign_rows(d_keys + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
         renderBatch(d_keys + b0, d_angles ? d_angles + b0 : nullptr, n, d_rowOfSlot_);
-        launch_publish_rows(d_keys + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
+        if (publish) launch_publish_rows(d_keys + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
+        if (rowsOut) {
+            IPP_CUDA_CHECK(cudaMemcpyAsync(rowsOut->data() + b0, d_rowOfSlot_, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            sync();
+        }
         nLaunches_ += 2;
     }
-    liveRows_ += nNew;
+    if (publish) liveRows_ += nNew;
 }
 
 int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx) {
@@ -575,13 +583,9 @@ int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offs
     return hi - lo;
 }
 
-// ---------------------------------------------------------------------------------------------
-void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t pop,
-                                         int64_t nGenes, bool memo, bool noLimit, double* d_fitness, uint32_t* unionBitmapHost) {
-    bind();
-    if (d_angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
-    if (pop <= 0) return;
-    requireQuickHeading();
+// Steps 1-2 of evaluatePlan for a population: collision flags never seen before -> K5, then energy, path length, colliding-edge
+// count and the energy gate (fitness rows, active flags).  Independent of heading offsets.
+void Evaluator::energyAndGate(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, double* d_fitness) {
     if (pop > activeCap_) {
         cudaFree(d_active_);
         activeCap_ = pop + pop / 4 + 16;
@@ -618,7 +622,22 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
     groupBegin(KG_PLAN);
     launch_energy(en, stream_);
     nLaunches_++;
+    groupEnd(KG_PLAN);
+}
 
+// ---------------------------------------------------------------------------------------------
+void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t pop,
+                                         int64_t nGenes, bool memo, bool noLimit, double* d_fitness, uint32_t* unionBitmapHost) {
+    bind();
+    if (d_angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
+    if (pop <= 0) return;
+    requireQuickHeading();
+    energyAndGate(d_ids, d_offsets, pop, noLimit, d_fitness);
+    PlanMarkArgs mk;
+    mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
+    mk.newKeys = d_newKeys_; mk.newCount = d_scalars_; mk.errFlag = d_scalars_ + 3; mk.used = nullptr;
+
+    groupBegin(KG_PLAN);
     // 3. edge bitmaps never seen before -> K3, K4, pack
     IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
     mk.active = d_active_; mk.coll = nullptr; mk.rowmap = d_rowmap_;
@@ -676,16 +695,188 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// [id, angleOffset] genes (SIMPLIFIED_VIEW_ANGLE = False, PlanInterpreterBoxOrder.cpp:278-299: the heading of the edge INTO a
+// viewpoint is turned by that viewpoint's offset, narrowed to float).  Energy, path length and collisions do not depend on the
+// offsets and take the common path; the edge bitmaps do, so their memo is keyed by (edge key, offset bits) -- the reference's
+// string key "prevID-currID,offset" (PlanCoverageEstimator.cpp:58-65) -- and lives on the host next to the integer-keyed one.
+// Host-pointer entry points only.
+// ---------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t angle_key(int key, float angle) {
+    uint32_t bits;
+    memcpy(&bits, &angle, 4);
+    return ((uint64_t)(uint32_t)key << 32) | bits;
+}
+}  // namespace
+
+void Evaluator::evaluatePopulationAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo, bool noLimit,
+                                         double* fitness, uint32_t* unionBitmap) {
+    const int64_t nGenes = offsets[pop];
+    for (int64_t g = 0; g < nGenes; ++g)
+        if (ids[g] < 0 || ids[g] >= N_) throw std::out_of_range("libipp: box id out of range");
+    energyAndGate(d_ids_, d_offsets_, pop, noLimit, d_fitness_);
+    std::vector<uint8_t> active(pop);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(active.data(), d_active_, (size_t)pop, cudaMemcpyDeviceToHost, stream_));
+    readScalars();  // also synchronises; [1] = free rows
+    const int freeRows = h_scalars_[1];
+
+    // the edges of the plans that passed the gate: memoised row, or a slot of this call's new (key, offset) pairs
+    std::vector<int64_t> edgeOffsets(pop + 1, 0);
+    std::vector<int> edgeRows;  // >= 0 row, < 0: -(slot + 1)
+    std::vector<int> newKeys;
+    std::vector<float> newAngles;
+    std::unordered_map<uint64_t, int> slotOf;
+    for (int64_t p = 0; p < pop; ++p) {
+        const int64_t lo = offsets[p], n = offsets[p + 1] - lo;
+        if (active[p] && n > 0) {
+            // node sequence [start] g_0 .. g_{n-1} [g_0 if the plan loops around]; the offset of an edge is its end node's
+            int prev = hasStart_ ? N_ : ids[lo];
+            const int64_t firstEnd = hasStart_ ? 0 : 1, ends = n + (loops_ ? 1 : 0);
+            for (int64_t k = firstEnd; k < ends; ++k) {
+                const int64_t gk = k < n ? k : 0;
+                const int cur = ids[lo + gk];
+                const float ang = angles[lo + gk];
+                const int key = prev * N_ + cur;
+                const uint64_t mk = angle_key(key, ang);
+                auto it = angleMemo_.find(mk);
+                if (it != angleMemo_.end()) {
+                    edgeRows.push_back(it->second);
+                } else {
+                    auto ins = slotOf.emplace(mk, (int)newKeys.size());
+                    if (ins.second) {
+                        newKeys.push_back(key);
+                        newAngles.push_back(ang);
+                    }
+                    edgeRows.push_back(-(ins.first->second + 1));
+                }
+                prev = cur;
+            }
+        }
+        edgeOffsets[p + 1] = (int64_t)edgeRows.size();
+    }
+    const int nNew = (int)newKeys.size();
+    if (nNew > freeRows)
+        throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
+                                 " free rows); call updateMemoisedEdges or evaluate a smaller batch");
+    // render the new pairs, at most nKeys_ at a time (the size of the key and offset staging buffers)
+    std::vector<int> newRows(nNew);
+    if (nNew > 0 && !d_angleBuf_) d_angleBuf_ = dalloc<float>(nKeys_);
+    for (int c0 = 0; c0 < nNew; c0 += nKeys_) {
+        const int n = std::min(nKeys_, nNew - c0);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_newKeys_, newKeys.data() + c0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_angleBuf_, newAngles.data() + c0, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        std::vector<int> rows;
+        renderKeys(d_newKeys_, n, d_angleBuf_, /*publish=*/false, &rows);
+        std::copy(rows.begin(), rows.end(), newRows.begin() + c0);
+    }
+    for (int& r : edgeRows)
+        if (r < 0) r = newRows[-r - 1];
+
+    // OR + area-weighted popcount through the explicit row list
+    const int64_t nEdges = (int64_t)edgeRows.size();
+    if (nEdges + 1 > edgeRowsCap_) {
+        cudaFree(d_edgeRows_);
+        edgeRowsCap_ = nEdges + nEdges / 4 + 16;
+        d_edgeRows_ = dalloc<int>(edgeRowsCap_);
+    }
+    if (pop + 2 > edgeOffCap_) {
+        cudaFree(d_edgeOffsets_);
+        edgeOffCap_ = pop + pop / 4 + 16;
+        d_edgeOffsets_ = dalloc<int64_t>(edgeOffCap_);
+    }
+    if (nEdges > 0) IPP_CUDA_CHECK(cudaMemcpyAsync(d_edgeRows_, edgeRows.data(), (size_t)nEdges * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_edgeOffsets_, edgeOffsets.data(), (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+    PlanReduceArgs rd;
+    rd.ids = d_ids_; rd.offsets = d_offsets_; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
+    rd.active = d_active_; rd.rowmap = d_rowmap_; rd.edgeRows = d_edgeRows_; rd.edgeOffsets = d_edgeOffsets_;
+    rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
+    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness_;
+    groupBegin(KG_REDUCE);
+    launch_plan_reduce(rd, numSMs_, stream_);
+    groupEnd(KG_REDUCE);
+    nLaunches_++;
+    nReduceLaunches_++;
+    nPlansReduced_ += pop;
+    IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, d_fitness_, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+
+    auto rowListToDevice = [&](const std::vector<int>& list) {
+        if ((int64_t)list.size() > rowListCap_) {
+            cudaFree(d_rowList_);
+            rowListCap_ = (int64_t)list.size() + (int64_t)list.size() / 4 + 16;
+            d_rowList_ = dalloc<int>(rowListCap_);
+        }
+        if (!list.empty()) IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowList_, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    };
+    if (unionBitmap) {
+        std::vector<int> uniq(edgeRows);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        rowListToDevice(uniq);
+        launch_union_row_list(d_rowList_, (int)uniq.size(), d_rows_, rowWords_, d_union_, stream_);
+        nLaunches_++;
+        IPP_CUDA_CHECK(cudaMemcpyAsync(unionBitmap, d_union_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
+    }
+    sync();
+    if (memo) {
+        for (const auto& kv : slotOf) angleMemo_[kv.first] = newRows[kv.second];
+    } else if (nNew > 0) {
+        // memoization == false: nothing rendered for this call is remembered (evaluatePlanInternal, PlanCoverageEstimator.cpp:128-151)
+        rowListToDevice(newRows);
+        launch_release_rows(d_rowList_, nNew, d_freeStack_, d_scalars_ + 1, stream_);
+        nLaunches_++;
+        sync();
+    }
+}
+
+int64_t Evaluator::updateMemoisedEdgesAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop) {
+    // keys of the raw population: "start-first" only exists with a start location and the loop-closing edge is never part of the
+    // set (PlanCoverageEstimator.cpp:284-310)
+    std::unordered_map<uint64_t, int> keep;
+    for (int64_t p = 0; p < pop; ++p) {
+        const int64_t lo = offsets[p], n = offsets[p + 1] - lo;
+        if (n <= 0) continue;
+        int prev = hasStart_ ? N_ : ids[lo];
+        for (int64_t k = hasStart_ ? 0 : 1; k < n; ++k) {
+            const int cur = ids[lo + k];
+            const uint64_t mk = angle_key(prev * N_ + cur, angles[lo + k]);
+            auto it = angleMemo_.find(mk);
+            if (it != angleMemo_.end()) keep.emplace(mk, it->second);
+            prev = cur;
+        }
+    }
+    std::vector<int> freed;
+    for (const auto& kv : angleMemo_)
+        if (!keep.count(kv.first)) freed.push_back(kv.second);
+    angleMemo_.swap(keep);
+    if (!freed.empty()) {
+        if ((int64_t)freed.size() > rowListCap_) {
+            cudaFree(d_rowList_);
+            rowListCap_ = (int64_t)freed.size() + (int64_t)freed.size() / 4 + 16;
+            d_rowList_ = dalloc<int>(rowListCap_);
+        }
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowList_, freed.data(), freed.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        launch_release_rows(d_rowList_, (int)freed.size(), d_freeStack_, d_scalars_ + 1, stream_);
+        nLaunches_++;
+        sync();
+    }
+    return (int64_t)angleMemo_.size();
+}
+
 void Evaluator::evaluatePopulationHost(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo,
                                        bool noLimit, double* fitness, uint32_t* unionBitmap) {
     bind();
     if (pop <= 0) return;
-    if (angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
     const int64_t nGenes = offsets[pop] - offsets[0];
     if (offsets[0] != 0) throw std::invalid_argument("libipp: offsets[0] must be 0");
     ensurePlanBuffers(pop, nGenes);
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_ids_, ids, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_offsets_, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+    if (angles) {
+        requireQuickHeading();
+        evaluatePopulationAngles(ids, angles, offsets, pop, memo, noLimit, fitness, unionBitmap);
+        return;
+    }
     evaluatePopulationDevice(d_ids_, nullptr, d_offsets_, pop, nGenes, memo, noLimit, d_fitness_, unionBitmap);
     IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, d_fitness_, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     sync();
@@ -693,19 +884,23 @@ void Evaluator::evaluatePopulationHost(const int32_t* ids, const float* angles, 
 
 int64_t Evaluator::updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop) {
     bind();
-    if (angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
     const int64_t nGenes = pop > 0 ? offsets[pop] : 0;
     for (int64_t g = 0; g < nGenes; ++g)
         if (ids[g] < 0 || ids[g] >= N_) throw std::out_of_range("libipp: box id out of range");
-    ensurePlanBuffers(std::max<int64_t>(pop, 1), std::max<int64_t>(nGenes, 1));
+    // One memo in the reference, two here: a population of [id, offset] genes keeps none of the integer-keyed edges and the
+    // other way round.
+    const int64_t zero = 0;
+    const int64_t keptAngles = angles ? updateMemoisedEdgesAngles(ids, angles, offsets, pop) : updateMemoisedEdgesAngles(nullptr, nullptr, &zero, 0);
+    const int64_t popInt = angles ? 0 : pop;
+    ensurePlanBuffers(std::max<int64_t>(popInt, 1), std::max<int64_t>(nGenes, 1));
     launch_fill_u8(d_used_, nKeys_, 0, stream_);
-    if (pop > 0) {
+    if (popInt > 0) {
         IPP_CUDA_CHECK(cudaMemcpyAsync(d_ids_, ids, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-        IPP_CUDA_CHECK(cudaMemcpyAsync(d_offsets_, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_offsets_, offsets, (size_t)(popInt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
         // keys of the raw population: "start-first" only exists with a start location and the loop-closing edge is
         // never part of the set (PlanCoverageEstimator.cpp:284-310)
         PlanMarkArgs mk;
-        mk.ids = d_ids_; mk.offsets = d_offsets_; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = false;
+        mk.ids = d_ids_; mk.offsets = d_offsets_; mk.pop = popInt; mk.N = N_; mk.hasStart = hasStart_; mk.loops = false;
         mk.active = nullptr; mk.coll = nullptr; mk.rowmap = nullptr; mk.used = d_used_; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
         mk.errFlag = d_scalars_ + 3;
         launch_mark_rows(mk, stream_);
@@ -715,7 +910,7 @@ int64_t Evaluator::updateMemoisedEdges(const int32_t* ids, const float* angles, 
     launch_gc_rows(d_rowmap_, d_used_, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
     nLaunches_ += 2;
     liveRows_ = readInt(d_scalars_ + 2);
-    return liveRows_;
+    return liveRows_ + keptAngles;
 }
 
 // InterpretPlan, PlanInterpreterBoxOrder.cpp:301-324 (host twin of the device decode; used for export only)

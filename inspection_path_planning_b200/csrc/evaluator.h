@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -47,7 +48,7 @@ class Evaluator {
     // population and hold the same memo contents (checked).  Returns the number of edges this rank rendered itself.
     int64_t renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx);
     int64_t updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
-    int64_t memoSize() const { return liveRows_; }
+    int64_t memoSize() const { return liveRows_ + (int64_t)angleMemo_.size(); }
     void clearMemo();
     void interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs) const;
 
@@ -88,7 +89,11 @@ class Evaluator {
 
    private:
     void renderNewEdges(int nNew, const float* d_angles);
-    void renderKeys(const int* d_keys, int n, const float* d_angles);
+    void renderKeys(const int* d_keys, int n, const float* d_angles, bool publish = true, std::vector<int>* rowsOut = nullptr);
+    void energyAndGate(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, double* d_fitness);
+    void evaluatePopulationAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo, bool noLimit,
+                                  double* fitness, uint32_t* unionBitmap);
+    int64_t updateMemoisedEdgesAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
     void renderSnapshots(int nSnaps, int32_t* d_idImage);
     void requireQuickHeading() const;
@@ -138,6 +143,13 @@ class Evaluator {
     BinBuffers bins_;
     int* d_superOffset_ = nullptr;
     int* d_countsAll_ = nullptr;  // snapshots per new edge (nKeys + 1)
+    // [id, angleOffset] genes: the memo of their edges lives on the host, key = (edge key << 32) | float bits of the offset
+    std::unordered_map<uint64_t, int> angleMemo_;
+    float* d_angleBuf_ = nullptr;   // nKeys
+    int* d_edgeRows_ = nullptr;
+    int64_t* d_edgeOffsets_ = nullptr;
+    int* d_rowList_ = nullptr;
+    int64_t edgeRowsCap_ = 0, edgeOffCap_ = 0, rowListCap_ = 0;
     // shared rendering across ranks
     int* d_sortedKeys_ = nullptr;  // nKeys
     void* d_sortTmp_ = nullptr;

@@ -123,18 +123,21 @@ int ipp_evaluate_plan(ipp_t* h, const double* genes, int n, int width, int memoi
     if (how_to_plot == IPP_PLOT_IMAGE)  // PlanCoverageEstimator.cpp:206-208
         throw std::logic_error("ERROR! Asked to plot image, but not given an OSG-drawable to plot to.");
     if (how_to_plot != IPP_PLOT_NOTHING) throw std::logic_error("libipp: only how_to_plot == nothing is supported (no GL viewers)");
-    if (width != 1) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
+    if (width != 1 && width != 2) throw std::invalid_argument("libipp: a gene is [id] or [id, angleOffset]");
     std::vector<int32_t> ids((size_t)n);
+    std::vector<float> angles((size_t)n, 0.f);
     for (int i = 0; i < n; ++i) {
         size_t id = (size_t)(genes[(size_t)i * width] + 0.5);  // PlanInterpreterBoxOrder.cpp:280 (a -1 gene decodes to 0)
         if (id >= (size_t)E(h).numBoxes()) throw std::out_of_range("libipp: box id out of range");
         ids[i] = (int32_t)id;
+        if (width == 2) angles[i] = (float)genes[(size_t)i * width + 1];  // float sensor_dir_offset, :283-286
     }
     int64_t off[2] = {0, n};
     if (n == 0) {
         out4[0] = 1.0; out4[1] = 0; out4[2] = 0; out4[3] = 0;  // evaluateEmptyPlan
     } else {
-        E(h).evaluatePopulationHost(ids.data(), nullptr, off, 1, memoization != 0, disable_energy_limit != 0, out4, nullptr);
+        E(h).evaluatePopulationHost(ids.data(), width == 2 ? angles.data() : nullptr, off, 1, memoization != 0, disable_energy_limit != 0, out4,
+                                    nullptr);
     }
     IPP_CATCH
 }

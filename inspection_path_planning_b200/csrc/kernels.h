@@ -41,6 +41,8 @@ struct PlanReduceArgs {
     bool hasStart, loops;
     const uint8_t* active;
     const int* rowmap;
+    const int* edgeRows = nullptr;         // optional ([id, angle] genes): row of edge e of plan p at edgeRows[edgeOffsets[p] + e],
+    const int64_t* edgeOffsets = nullptr;  // instead of rowmap[key]
     const uint32_t* rows;  // row pool
     int64_t rowWords;      // words per row (multiple of 4)
     const double* area;    // padded to nTiles * kTileTris
@@ -119,6 +121,9 @@ void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t 
 void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st);
 void launch_union_rows(const uint8_t* d_used, int nKeys, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union,
                        cudaStream_t st);
+// OR of an explicit list of rows -> union bitmap; rows back to the free stack
+void launch_union_row_list(const int* d_rowList, int n, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union, cudaStream_t st);
+void launch_release_rows(const int* d_rowList, int n, int* d_freeStack, int* d_freeTop, cudaStream_t st);
 void launch_fill_u8(uint8_t* p, int64_t n, uint8_t v, cudaStream_t st);
 void launch_fill_i32(int* p, int64_t n, int v, cudaStream_t st);
 void launch_iota_i32(int* p, int64_t n, cudaStream_t st);

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kThreads) k_plan_reduce(PlanReduceArgs a) {
         };
         auto rowOfEdge = [&](int e) -> int {  // edge e joins positions e and e + 1
             if (e >= nEdges) return -1;
+            if (a.edgeRows) return a.edgeRows[a.edgeOffsets[p] + e];
             return a.rowmap[boxAt(e) * a.N + boxAt(e + 1)];
         };
         // an area tile is needed by the CTA if any of its plans is active
@@ -154,6 +155,19 @@ __global__ void k_union_rows(const uint8_t* __restrict__ used, int nKeys, const 
     out[w] = acc;
 }
 
+__global__ void k_union_row_list(const int* __restrict__ rowList, int n, const uint32_t* __restrict__ rows, long long rowWords,
+                                 uint32_t* __restrict__ out) {
+    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= rowWords) return;
+    uint32_t acc = 0;
+    for (int k = 0; k < n; ++k) acc |= rows[(size_t)rowList[k] * rowWords + w];
+    out[w] = acc;
+}
+__global__ void k_release_rows(const int* __restrict__ rowList, int n, int* __restrict__ freeStack, int* __restrict__ freeTop) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) freeStack[atomicAdd(freeTop, 1)] = rowList[i];
+}
+
 __global__ void k_fill_u8(uint8_t* p, long long n, uint8_t v) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -191,6 +205,12 @@ void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st) {
 void launch_union_rows(const uint8_t* d_used, int nKeys, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union,
                        cudaStream_t st) {
     k_union_rows<<<(unsigned)((rowWords + 127) / 128), 128, 0, st>>>(d_used, nKeys, d_rowmap, d_rows, (long long)rowWords, d_union);
+}
+void launch_union_row_list(const int* d_rowList, int n, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union, cudaStream_t st) {
+    k_union_row_list<<<(unsigned)((rowWords + 127) / 128), 128, 0, st>>>(d_rowList, n, d_rows, (long long)rowWords, d_union);
+}
+void launch_release_rows(const int* d_rowList, int n, int* d_freeStack, int* d_freeTop, cudaStream_t st) {
+    if (n > 0) k_release_rows<<<(n + 255) / 256, 256, 0, st>>>(d_rowList, n, d_freeStack, d_freeTop);
 }
 void launch_fill_u8(uint8_t* p, int64_t n, uint8_t v, cudaStream_t st) {
     if (n > 0) k_fill_u8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, (long long)n, v);

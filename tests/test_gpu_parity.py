@@ -595,8 +595,60 @@ def test_zero_angle_genes_evaluate_like_plain_ids(sphere):
     with_zero = [[100, 0], [101, 0.0], [113, 0]]
     assert g.evaluatePlan(with_zero, True, cb.nothing) == g.evaluatePlan(plan, True, cb.nothing)
     assert np.array_equal(g.evaluatePopulation([with_zero], True, False), g.evaluatePopulation([plan], True, False))
-    with pytest.raises(NotImplementedError):
-        g.evaluatePlan([[100, 0.3], [101, 0]], True, cb.nothing)
+
+
+def _angle_plans(rng, n_boxes, pop, length):
+    plans = random_plans(rng, n_boxes, pop, length)
+    return [[[gene[0], float(rng.uniform(-1.0, 1.0)) if rng.random() < 0.7 else 0.0] for gene in p] for p in plans]
+
+
+def _close_up_to_one_triangle(got, want, o):
+    np.testing.assert_allclose(got[:, 1:3], want[:, 1:3], rtol=ENERGY_RTOL, atol=0)
+    assert np.array_equal(got[:, 3], want[:, 3])
+    one = o.areas().max() / o.total_area()
+    assert np.abs(got[:, 0] - want[:, 0]).max() <= one * 1.000001 + 1e-9
+    assert np.isclose(got[:, 0], want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9).mean() > 0.9
+
+
+@pytest.mark.parametrize("with_start_and_loop", [False, True])
+def test_angle_offset_genes_match_the_oracle(oracle_mod, with_start_and_loop):
+    """[id, angleOffset] genes (SIMPLIFIED_VIEW_ANGLE = False): heading of the edge into a viewpoint turned by its offset; memo keyed
+    by (previous id, id, offset) like the reference's string key."""
+    from inspection_path_planning_b200 import cpp_binding as cb
+    kw = dict(start=[6.0, 6.0, 8.0], loops=True) if with_start_and_loop else {}
+    g, o = _pair(oracle_mod, "sphere", 64, **kw)
+    try:
+        rng = np.random.default_rng(91)
+        plans = _angle_plans(rng, o.getNumberOfBoxes(), 24, (2, 6)) + [[]]
+        g.counters(reset=True)
+        got = g.evaluatePopulation(plans, True, True)
+        want = o.evaluatePopulation(plans, True, True)
+        _close_up_to_one_triangle(got, want, o)
+        assert got[-1].tolist() == [1.0, 0.0, 0.0, 0.0]
+        assert g.memo_size() == o.memo_size() > 0
+        rendered = g.counters()["edges_rendered"]
+        # the turned heading matters: the same plans with the offsets dropped score differently somewhere
+        plain = g.evaluatePopulation([[[gene[0]] for gene in p] for p in plans], True, True)
+        assert np.abs(plain[:, 0] - got[:, 0]).max() > 1e-3 and np.array_equal(plain[:, 1:], got[:, 1:])
+        # warm: same rows, nothing rendered; single-plan call = its row
+        g.counters(reset=True)
+        assert np.array_equal(g.evaluatePopulation(plans, True, True), got)
+        assert g.counters()["edges_rendered"] == 0
+        assert g.evaluatePlan(plans[3], True, cb.nothing, True) == (got[3, 0], got[3, 1])
+        # with the energy limit on, gated plans score exactly 1 and render nothing
+        lim_g, lim_o = g.evaluatePopulation(plans, True, False), o.evaluatePopulation(plans, True, False)
+        assert np.array_equal(lim_g[:, 0] == 1.0, lim_o[:, 0] == 1.0)
+        # memo garbage collection by a sub-population, reference count
+        keep = plans[:7]
+        assert g.updateMemoisedEdges(keep) == o.updateMemoisedEdges(keep)
+        assert g.memo_size() == o.memo_size()
+        # memoization == false leaves the memo as it was
+        before = g.memo_size()
+        nomemo = g.evaluatePopulation(plans[7:12], False, True)
+        assert np.array_equal(nomemo, got[7:12]) and g.memo_size() == before
+        assert rendered > 0
+    finally:
+        g.close()
 
 
 def test_tiny_meshes_one_triangle_and_a_twelve_triangle_box(oracle_mod, tmp_path):
