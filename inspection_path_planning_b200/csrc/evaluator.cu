@@ -216,6 +216,7 @@ Evaluator::~Evaluator() {
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
     cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
     cudaFree(bins_.scratch); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
+    cudaFree(d_pseudoOffsets_); cudaFree(d_pseudoEdgeOffsets_); cudaFree(d_pseudoActive_); cudaFree(d_pseudoFitness_);
     cudaFree(d_angleBuf_); cudaFree(d_edgeRows_); cudaFree(d_edgeOffsets_); cudaFree(d_rowList_);
     cudaFree(d_sortedKeys_); cudaFree(d_sortTmp_); cudaFree(d_exchange_); cudaFree(d_activeShared_); cudaFree(d_fitShared_);
     cudaFree(d_ids_); cudaFree(d_offsets_); cudaFree(d_fitness_); cudaFree(d_active_); cudaFree(d_union_);
@@ -434,6 +435,7 @@ void Evaluator::clearMemo() {
     nLaunches_ += 3;
     liveRows_ = 0;
     angleMemo_.clear();
+    headingReversed_.clear();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,7 +633,6 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
     bind();
     if (d_angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
     if (pop <= 0) return;
-    requireQuickHeading();
     energyAndGate(d_ids, d_offsets, pop, noLimit, d_fitness);
     PlanMarkArgs mk;
     mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
@@ -657,7 +658,8 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
         if (nNew > freeRows)
             throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
                                      " free rows); call updateMemoisedEdges or evaluate a smaller batch");
-        renderNewEdges(nNew, nullptr);
+        if (postProcessing_) renderKeysHeadingSearch(d_newKeys_, nNew);
+        else renderNewEdges(nNew, nullptr);
     }
 
     // 4. OR + area-weighted popcount
@@ -913,22 +915,132 @@ int64_t Evaluator::updateMemoisedEdges(const int32_t* ids, const float* angles, 
     return liveRows_ + keptAngles;
 }
 
+// ---------------------------------------------------------------------------------------------
+// postProcessing = true: calculateViewingDirectionTowardsPrimitives (OsgHelpers.cpp:451-489).  The heading of an edge keeps the
+// axis of the quick rule but its side is chosen by looking: both candidates are rendered along the edge (K4, the second one
+// through the +infinity sentinel of sensor_direction), K6 turns each bitmap into its coverage score (pseudo plans of one edge),
+// the lower score wins and a tie keeps the quick heading.  The winner's bitmap IS the bitmap of the edge (the reference renders
+// it once more with the same heading); the loser's row goes back to the free stack.
+// ---------------------------------------------------------------------------------------------
+void Evaluator::renderKeysHeadingSearch(const int* d_keys, int nNew) {
+    if (nNew <= 0) return;
+    if (!d_sortedKeys_) d_sortedKeys_ = dalloc<int>(nKeys_);
+    if (!d_angleBuf_) d_angleBuf_ = dalloc<float>(nKeys_);
+    const int chunkMax = std::max(1, std::min(nKeys_ / 2, batchCap_));
+    std::vector<int> keys(nNew);
+    IPP_CUDA_CHECK(cudaMemcpyAsync(keys.data(), d_keys, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    sync();
+    for (int c0 = 0; c0 < nNew; c0 += chunkMax) {
+        const int C = std::min(chunkMax, nNew - c0), C2 = 2 * C;
+        std::vector<int> keys2(C2);
+        std::vector<float> ang2(C2);
+        for (int i = 0; i < C; ++i) {
+            keys2[2 * i] = keys2[2 * i + 1] = keys[c0 + i];
+            ang2[2 * i] = 0.f;
+            ang2[2 * i + 1] = INFINITY;
+        }
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_sortedKeys_, keys2.data(), (size_t)C2 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_angleBuf_, ang2.data(), (size_t)C2 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        std::vector<int> rows;
+        renderKeys(d_sortedKeys_, C2, d_angleBuf_, /*publish=*/false, &rows);
+        // coverage score of every candidate bitmap: C2 pseudo plans of one edge each through K6
+        if (C2 > pseudoCap_) {
+            cudaFree(d_pseudoOffsets_); cudaFree(d_pseudoEdgeOffsets_); cudaFree(d_pseudoActive_); cudaFree(d_pseudoFitness_);
+            pseudoCap_ = C2 + C2 / 4 + 16;
+            d_pseudoOffsets_ = dalloc<int64_t>(pseudoCap_ + 1);
+            d_pseudoEdgeOffsets_ = dalloc<int64_t>(pseudoCap_ + 1);
+            d_pseudoActive_ = dalloc<uint8_t>(pseudoCap_);
+            d_pseudoFitness_ = dalloc<double>((size_t)pseudoCap_ * 4);
+            std::vector<int64_t> off(pseudoCap_ + 1), eoff(pseudoCap_ + 1);
+            for (int i = 0; i <= pseudoCap_; ++i) { off[i] = 2 * (int64_t)i; eoff[i] = i; }
+            IPP_CUDA_CHECK(cudaMemcpyAsync(d_pseudoOffsets_, off.data(), off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+            IPP_CUDA_CHECK(cudaMemcpyAsync(d_pseudoEdgeOffsets_, eoff.data(), eoff.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
+            launch_fill_u8(d_pseudoActive_, pseudoCap_, 1, stream_);
+            sync();
+        }
+        if (C2 + 1 > edgeRowsCap_) {
+            cudaFree(d_edgeRows_);
+            edgeRowsCap_ = C2 + C2 / 4 + 16;
+            d_edgeRows_ = dalloc<int>(edgeRowsCap_);
+        }
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_edgeRows_, rows.data(), (size_t)C2 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        PlanReduceArgs rd;
+        rd.ids = d_sortedKeys_; rd.offsets = d_pseudoOffsets_; rd.pop = C2; rd.N = N_; rd.hasStart = false; rd.loops = false;
+        rd.active = d_pseudoActive_; rd.rowmap = d_rowmap_; rd.edgeRows = d_edgeRows_; rd.edgeOffsets = d_pseudoEdgeOffsets_;
+        rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
+        rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_pseudoFitness_;
+        launch_plan_reduce(rd, numSMs_, stream_);
+        nLaunches_++;
+        std::vector<double> fit((size_t)C2 * 4);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(fit.data(), d_pseudoFitness_, fit.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        sync();
+        std::vector<int> winners(C), losers(C);
+        for (int i = 0; i < C; ++i) {
+            const double quick = fit[(size_t)(2 * i) * 4], reversed = fit[(size_t)(2 * i + 1) * 4];
+            const bool rev = reversed < quick;  // lower score = more surface seen; a tie keeps the quick heading
+            winners[i] = rows[2 * i + (rev ? 1 : 0)];
+            losers[i] = rows[2 * i + (rev ? 0 : 1)];
+            headingReversed_[keys[c0 + i]] = rev;
+        }
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowOfSlot_, winners.data(), (size_t)C * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        launch_publish_rows(d_keys + c0, d_rowOfSlot_, C, d_rowmap_, stream_);
+        if ((int64_t)C > rowListCap_) {
+            cudaFree(d_rowList_);
+            rowListCap_ = C + C / 4 + 16;
+            d_rowList_ = dalloc<int>(rowListCap_);
+        }
+        IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowList_, losers.data(), (size_t)C * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        launch_release_rows(d_rowList_, C, d_freeStack_, d_scalars_ + 1, stream_);
+        nLaunches_ += 2;
+        sync();
+        liveRows_ += C;
+    }
+}
+
+// headings of keys the memo does not hold yet (interpretAndExportPlan of a post-processing evaluator)
+void Evaluator::decideHeadings(const std::vector<int>& keys) {
+    std::vector<int> todo;
+    for (int k : keys)
+        if (!headingReversed_.count(k) && std::find(todo.begin(), todo.end(), k) == todo.end()) todo.push_back(k);
+    if (todo.empty()) return;
+    bind();
+    readScalars();
+    if ((int)todo.size() * 2 > h_scalars_[1]) throw std::runtime_error("libipp: edge-bitmap cache full; call updateMemoisedEdges");
+    IPP_CUDA_CHECK(cudaMemcpyAsync(d_newKeys_, todo.data(), todo.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    renderKeysHeadingSearch(d_newKeys_, (int)todo.size());
+}
+
 // InterpretPlan, PlanInterpreterBoxOrder.cpp:301-324 (host twin of the device decode; used for export only)
-void Evaluator::interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs) const {
+void Evaluator::interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs) {
     *nPos = 0;
     *nDirs = 0;
     if (n == 0) return;
-    requireQuickHeading();
     D3 center = d3(sceneCenter_[0], sceneCenter_[1], sceneCenter_[2]);
+    std::vector<int> idx;  // position sequence as box indices (N_ = start location)
+    if (hasStart_) idx.push_back(N_);
+    for (int i = 0; i < n; ++i) {
+        size_t id = (size_t)(genes[(size_t)i * width] + 0.5);
+        if (id >= (size_t)N_) throw std::out_of_range("libipp: box id out of range");
+        idx.push_back((int)id);
+    }
+    if (postProcessing_) {
+        if (width > 1) throw std::invalid_argument("libipp: [id, angle] genes are not supported together with postProcessing = true");
+        std::vector<int> keys;
+        for (size_t k = 1; k < idx.size(); ++k) keys.push_back(idx[k - 1] * N_ + idx[k]);
+        decideHeadings(keys);
+    }
     std::vector<D3> p;
     if (hasStart_) p.push_back(d3(start_[0], start_[1], start_[2]));
     int nd = 0;
     for (int i = 0; i < n; ++i) {
-        size_t id = (size_t)(genes[(size_t)i * width] + 0.5);
-        if (id >= (size_t)N_) throw std::out_of_range("libipp: box id out of range");
+        const int id = idx[i + (hasStart_ ? 1 : 0)];
         float off = width > 1 ? (float)genes[(size_t)i * width + 1] : 0.f;
-        D3 cur = d3(grid_.centres[3 * id], grid_.centres[3 * id + 1], grid_.centres[3 * id + 2]);
+        D3 cur = d3(grid_.centres[3 * (size_t)id], grid_.centres[3 * (size_t)id + 1], grid_.centres[3 * (size_t)id + 2]);
         if (!p.empty()) {
+            if (postProcessing_) {
+                const int prevIdx = idx[i + (hasStart_ ? 1 : 0) - 1];
+                off = headingReversed_.at(prevIdx * N_ + id) ? INFINITY : 0.f;
+            }
             D3 h = sensor_direction(p.back(), cur, center, off);
             dirs[3 * nd] = h.x; dirs[3 * nd + 1] = h.y; dirs[3 * nd + 2] = h.z;
             nd++;
@@ -943,13 +1055,12 @@ void Evaluator::interpretPlan(const double* genes, int n, int width, double* pos
 // ---------------------------------------------------------------------------------------------
 // test hooks
 // ---------------------------------------------------------------------------------------------
-// postProcessing = true switches the reference to calculateViewingDirectionTowardsPrimitives (OsgHelpers.cpp:451-489): both
-// candidate headings of every edge are rendered and the one that covers more wins.  That mode is not built;
-// answering with the quick heading instead would be a silent change of results, so every heading-dependent call refuses.
+// What a post-processing evaluator does not do: [id, angle] genes, the per-edge test hook and the multi-GPU edge sharing keep the
+// quick heading rule and refuse instead of answering with it.
 void Evaluator::requireQuickHeading() const {
     if (postProcessing_)
-        throw std::logic_error("libipp: postProcessing = true (heading search towards the primitives) is not implemented; construct the "
-                               "evaluator with postProcessing = false");
+        throw std::logic_error("libipp: not available with postProcessing = true (heading search towards the primitives): [id, angle] "
+                               "genes, ipp_edge_bitmap and the multi-GPU edge sharing use the quick heading rule");
 }
 
 void Evaluator::edgeBitmap(int prev, int curr, double angle, uint32_t* out) {

@@ -50,7 +50,7 @@ class Evaluator {
     int64_t updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
     int64_t memoSize() const { return liveRows_ + (int64_t)angleMemo_.size(); }
     void clearMemo();
-    void interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs) const;
+    void interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs);
 
     // ---- test hooks ----
     void edgeBitmap(int prev, int curr, double angle, uint32_t* out);
@@ -97,6 +97,9 @@ class Evaluator {
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
     void renderSnapshots(int nSnaps, int32_t* d_idImage);
     void requireQuickHeading() const;
+    // postProcessing = true: both candidate headings of every key are rendered, the better one becomes the memo row
+    void renderKeysHeadingSearch(const int* d_keys, int n);
+    void decideHeadings(const std::vector<int>& keys);
     void ensurePlanBuffers(int64_t pop, int64_t nGenes);
     void ensureSnapBuffers(int64_t nSnaps);
     int readInt(const int* d);
@@ -150,6 +153,13 @@ class Evaluator {
     int64_t* d_edgeOffsets_ = nullptr;
     int* d_rowList_ = nullptr;
     int64_t edgeRowsCap_ = 0, edgeOffCap_ = 0, rowListCap_ = 0;
+    // postProcessing = true: which keys ended up with the reversed heading (calculateViewingDirectionTowardsPrimitives)
+    std::unordered_map<int, bool> headingReversed_;
+    int64_t* d_pseudoOffsets_ = nullptr;
+    int64_t* d_pseudoEdgeOffsets_ = nullptr;
+    uint8_t* d_pseudoActive_ = nullptr;
+    double* d_pseudoFitness_ = nullptr;
+    int pseudoCap_ = 0;
     // shared rendering across ranks
     int* d_sortedKeys_ = nullptr;  // nKeys
     void* d_sortTmp_ = nullptr;

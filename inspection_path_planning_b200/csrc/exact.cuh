@@ -160,9 +160,14 @@ IPP_HD D3 viewing_direction(const D3& a, const D3& b, const D3& center) {
     }
     return d;
 }
-// calculateSensorDirectionAndNormalize, PE/PlanInterpreterBoxOrder.cpp:258-276 (quick mode)
+// calculateSensorDirectionAndNormalize, PE/PlanInterpreterBoxOrder.cpp:258-276.  offset = +infinity is the sentinel of the
+// post-processing heading search (OsgHelpers.cpp:451-489): the other candidate, i.e. the quick heading reversed, no offset.
 IPP_HD D3 sensor_direction(const D3& prev, const D3& next, const D3& center, float offset) {
     D3 d = viewing_direction(prev, next, center);
+    if (offset > 3.0e38f) {
+        d = -d;
+        offset = 0.f;
+    }
     normalize(d);
     double rad = atan2(d.y, d.x);
     rad += offset;

@@ -170,7 +170,8 @@ int ipp_clear_memo(ipp_t* h) {
 
 int ipp_interpret_plan(const ipp_t* h, const double* genes, int n, int width, double* pos, double* dirs, int* n_pos, int* n_dirs) {
     IPP_TRY
-    E(h).interpretPlan(genes, n, width, pos, dirs, n_pos, n_dirs);
+    // (a post-processing evaluator may have to render the edges of the plan to decide their headings: not const underneath)
+    const_cast<Evaluator&>(E(h)).interpretPlan(genes, n, width, pos, dirs, n_pos, n_dirs);
     IPP_CATCH
 }
 

@@ -394,9 +394,9 @@ def load_dumped_population(path):
         return yaml.safe_load(f)
 
 
-def make_evaluator(scene, params):
+def make_evaluator(scene, params, post_processing=False):
     from . import cpp_binding
-    return cpp_binding.PlanCoverageEstimator(scene, params.SENSOR_PARAMETERS, False, params.PLAN_ORIGIN, params.PLAN_LOOPS_AROUND, True)
+    return cpp_binding.PlanCoverageEstimator(scene, params.SENSOR_PARAMETERS, post_processing, params.PLAN_ORIGIN, params.PLAN_LOOPS_AROUND, True)
 
 
 def main(argv=None):

@@ -9,11 +9,9 @@ The first waypoint carries a dummy orientation (the way to it is not part of the
 followed on the way to it, as yaw only (settings/Utilities.py:268-284).  Optional rotation about +z (degrees) is applied to
 positions and headings before the position offset, as the reference does.
 
-Difference to the reference: its exporter builds the evaluator with postProcessing=True (evolutionary_operators/
-planEvaluatorSetup.py:13-24), i.e. every exported heading comes from the heading search towards the primitives
-(OsgHelpers.cpp:451-489: render both perpendicular directions, keep the one that covers more).  That search is not built here
-(SURVEY 8(f) N4); this exporter writes the headings the optimiser evaluated the plan with (calculateViewingDirection, flipped
-towards the scene centre), which is the same axis and may be the opposite sign on edges where the far side shows more surface.
+Like the reference's exporter (evolutionary_operators/planEvaluatorSetup.py:13-24) export_all_winner_individuals builds the
+evaluator with postProcessing=True: every exported heading comes from the heading search towards the primitives
+(OsgHelpers.cpp:451-489: render both perpendicular directions along the edge, keep the one that shows more surface).
 
 The reference's sharp-turn splitting
 (split_sharply_turning_waypoints, :37-81) calls a split_waypoint() that is defined nowhere in its tree; it is not restated.
@@ -74,7 +72,7 @@ def export_all_winner_individuals(results_root, position_offsets=None, rotation_
     data = oc.load_dumped_population(src)
     if evaluator is None:
         params = oc.Parameters(SENSOR_PARAMETERS=data["sensor_params"], PLAN_ORIGIN=data["plan_origin"], PLAN_LOOPS_AROUND=data["plan_loops_around"])
-        evaluator = oc.make_evaluator(data["scene"], params)
+        evaluator = oc.make_evaluator(data["scene"], params, post_processing=True)
     out_dir = os.path.join(results_root, "plan_ymls")
     os.makedirs(out_dir, exist_ok=True)
     paths = []

@@ -618,9 +618,29 @@ struct Oracle {
         }
         return d;
     }
-    // PE/PlanInterpreterBoxOrder.cpp:258-276 (post-processing heading mode is out of scope)
-    V3 sensor_direction(const V3& prev, const V3& next, float offset) const {
-        V3 d = viewing_direction(prev, next);
+    // UF/OsgHelpers.cpp:451-489 (calculateViewingDirectionTowardsPrimitives): the same axis as viewing_direction, but the side is
+    // chosen by looking -- both candidate headings are rendered along the edge and the one with the lower coverage score wins; a
+    // tie falls back to viewing_direction.  The candidates are passed on unnormalised, as the reference does.
+    V3 viewing_direction_towards_primitives(const V3& a, const V3& b) {
+        V3 d;
+        if (a.x == b.x && a.y == b.y) {
+            d = sceneCenter - ((b + a) / 2.0);
+            d.z = 0;
+        } else {
+            d = cross(v3(0, 0, 1), b - a);
+        }
+        V3 r = -d;
+        Bits c1(W32(), 0), c2(W32(), 0);
+        colors_during_traversal(a, b, d, c1);
+        double s1 = coverage_score(c1);
+        colors_during_traversal(a, b, r, c2);
+        double s2 = coverage_score(c2);
+        if (s2 == s1) return viewing_direction(a, b);
+        return s2 > s1 ? d : r;
+    }
+    // PE/PlanInterpreterBoxOrder.cpp:258-276
+    V3 sensor_direction(const V3& prev, const V3& next, float offset) {
+        V3 d = postProcessing ? viewing_direction_towards_primitives(prev, next) : viewing_direction(prev, next);
         normalize(d);
         double rad = std::atan2(d.y, d.x);
         rad += offset;
@@ -628,7 +648,7 @@ struct Oracle {
         normalize(d);
         return d;
     }
-    void interpret_one(const V3* prev, const double* gene, int width, std::vector<V3>& pos, std::vector<V3>& dirs) const {
+    void interpret_one(const V3* prev, const double* gene, int width, std::vector<V3>& pos, std::vector<V3>& dirs) {
         size_t id = gene_id(gene[0]);
         float off = 0;
         if (width > 1) off = (float)gene[1];
@@ -636,7 +656,7 @@ struct Oracle {
         pos.push_back(cur);
         if (prev) dirs.push_back(sensor_direction(*prev, cur, off));
     }
-    void interpret_plan(const std::vector<std::vector<double>>& plan, std::vector<V3>& pos, std::vector<V3>& dirs) const {
+    void interpret_plan(const std::vector<std::vector<double>>& plan, std::vector<V3>& pos, std::vector<V3>& dirs) {
         if (plan.empty()) return;
         if (hasStart) pos.push_back(start);
         for (const auto& g : plan) {

@@ -574,18 +574,42 @@ def test_mesh_ingest_stl_and_obj_match_the_oracle_loader(oracle_mod, tmp_path):
         cpp_binding.PlanCoverageEstimator(__file__, sp)
 
 
-def test_post_processing_mode_refuses_instead_of_answering_with_the_quick_heading():
+@pytest.mark.parametrize("mesh,height,n_plans", [("sphere", 64, 16), ("mockup_only", 128, 6)])
+def test_post_processing_heading_search_matches_the_oracle(oracle_mod, mesh, height, n_plans):
+    """postProcessing = true: calculateViewingDirectionTowardsPrimitives -- both candidate headings of an edge are rendered, the one
+    that shows more surface wins, a tie keeps the quick rule (OsgHelpers.cpp:451-489)."""
     from inspection_path_planning_b200 import cpp_binding
-    g = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), specs(64), True)
+    sp = specs(height)
+    g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), sp, True)
+    o = oracle_mod.Oracle(mesh_path(mesh), sp, post_processing=True)
+    q = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), sp, False)
     try:
-        assert g.getMaxAllowedEnergy() == -1 and g.getNumberOfBoxes() > 0
-        assert g.evaluatePlan([], True, cpp_binding.nothing) == (1.0, 0.0)  # the empty plan needs no heading
-        for call in (lambda: g.evaluatePlan([[1], [2]], True, cpp_binding.nothing), lambda: g.evaluatePopulation([[[1], [2]]], True, True),
-                     lambda: g.interpretAndExportPlan([[1], [2]])):
-            with pytest.raises(RuntimeError, match="postProcessing"):
-                call()
+        assert g.getMaxAllowedEnergy() == o.getMaxAllowedEnergy() == -1
+        assert g.evaluatePlan([], True, cpp_binding.nothing) == (1.0, 0.0)
+        rng = np.random.default_rng(95)
+        plans = random_plans(rng, o.getNumberOfBoxes(), n_plans, (2, 5))
+        got = g.evaluatePopulation(plans, True, False)
+        want = o.evaluatePopulation(plans, True, False)
+        _close_up_to_one_triangle(got, want, o, min_close=0.75)  # (one edge-epsilon triangle on one of six plans at 128 px)
+        # every edge shows at least what the quick heading shows (the quick heading is one of the two candidates)
+        quick = q.evaluatePopulation(plans, True, True)
+        assert np.all(got[:, 0] <= quick[:, 0] + 1e-12) and np.array_equal(got[:, 1:], quick[:, 1:])
+        for p in plans[:6]:
+            gp, gd = g.interpretAndExportPlan(p)
+            op, od = o.interpretAndExportPlan(p)
+            assert gp == op
+            np.testing.assert_allclose(gd, od, atol=1e-12)
+        # a plan never evaluated before: its headings are decided on demand
+        fresh = [[3], [40], [77]]
+        np.testing.assert_allclose(g.interpretAndExportPlan(fresh)[1], o.interpretAndExportPlan(fresh)[1], atol=1e-12)
+        # what the mode does not do
+        with pytest.raises(RuntimeError, match="postProcessing"):
+            g.evaluatePlan([[1, 0.2], [2, 0.0]], True, cpp_binding.nothing)
+        with pytest.raises(RuntimeError, match="postProcessing"):
+            g.edge_bitmap(1, 2)
     finally:
         g.close()
+        q.close()
 
 
 def test_zero_angle_genes_evaluate_like_plain_ids(sphere):
@@ -602,12 +626,12 @@ def _angle_plans(rng, n_boxes, pop, length):
     return [[[gene[0], float(rng.uniform(-1.0, 1.0)) if rng.random() < 0.7 else 0.0] for gene in p] for p in plans]
 
 
-def _close_up_to_one_triangle(got, want, o):
+def _close_up_to_one_triangle(got, want, o, min_close=0.9):
     np.testing.assert_allclose(got[:, 1:3], want[:, 1:3], rtol=ENERGY_RTOL, atol=0)
     assert np.array_equal(got[:, 3], want[:, 3])
     one = o.areas().max() / o.total_area()
     assert np.abs(got[:, 0] - want[:, 0]).max() <= one * 1.000001 + 1e-9
-    assert np.isclose(got[:, 0], want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9).mean() > 0.9
+    assert np.isclose(got[:, 0], want[:, 0], rtol=COVERAGE_RTOL, atol=1e-9).mean() >= min_close
 
 
 @pytest.mark.parametrize("with_start_and_loop", [False, True])
