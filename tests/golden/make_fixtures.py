@@ -21,6 +21,9 @@ ASSETS = {
     "mockup_only.ippm": "mockup_only.stl",
     "luis4.ippm": "luis4.obj",
     "luis1.ippm": "luis1.obj",
+    "luis2.ippm": "luis2.obj",
+    "luis3.ippm": "luis3.obj",
+    "luis5.ippm": "luis5.obj",
     "sphere.ippm": "simple_shapes/sphere.obj",
 }
 

@@ -2,7 +2,7 @@
 
     python tools/run_configs.py c1        cube 12 288 triangles, NSGA-II pop 100 x 20 generations (optimize_coverage.py flow)
     python tools/run_configs.py c3 [pop]  luis4.obj (stand-in for oil_manifold.stl), pop x 30-viewpoint plans, cold + warm
-    python tools/run_configs.py c4 [pop]  luis1 + luis4 (the fixtures shipped here of the luis1..5 batch), pop plans of 2..15 viewpoints each, setup included
+    python tools/run_configs.py c4 [pop]  luis1..5 one after the other (multiRun.py style), pop plans of 2..15 viewpoints each, setup included
     python tools/run_configs.py c5 [lvl]  displaced icosphere (20 * 4^lvl triangles), 1 000 x 50-viewpoint plans (BVH-walk variant above 16 384 leaves)
 """
 import json
@@ -75,7 +75,7 @@ def c3(pop=2000):
 
 def c4(pop=1000):
     t0 = time.perf_counter()
-    for name in ("luis1", "luis4"):
+    for name in ("luis1", "luis2", "luis3", "luis4", "luis5"):
         t = time.perf_counter()
         g = cpp_binding.PlanCoverageEstimator(os.path.join(MESHES, name + ".ippm"), SPECS)
         setup = time.perf_counter() - t
