@@ -216,6 +216,7 @@ Evaluator::~Evaluator() {
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
     cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
     cudaFree(bins_.scratch); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
+    cudaFree(d_partial_);
     cudaFree(d_pseudoOffsets_); cudaFree(d_pseudoEdgeOffsets_); cudaFree(d_pseudoActive_); cudaFree(d_pseudoFitness_);
     cudaFree(d_angleBuf_); cudaFree(d_edgeRows_); cudaFree(d_edgeOffsets_); cudaFree(d_rowList_);
     cudaFree(d_sortedKeys_); cudaFree(d_sortTmp_); cudaFree(d_exchange_); cudaFree(d_activeShared_); cudaFree(d_fitShared_);
@@ -585,6 +586,17 @@ int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offs
     return hi - lo;
 }
 
+double* Evaluator::reducePartials(int64_t pop) {
+    if (nTiles_ <= 8 || pop > (int64_t)numSMs_ * 8 * 2) return nullptr;  // (launch_plan_reduce splits below two plan groups per SM)
+    const int64_t need = pop * nTiles_;
+    if (need > partialCap_) {
+        cudaFree(d_partial_);
+        partialCap_ = need + need / 4 + 16;
+        d_partial_ = dalloc<double>(partialCap_);
+    }
+    return d_partial_;
+}
+
 // Steps 1-2 of evaluatePlan for a population: collision flags never seen before -> K5, then energy, path length, colliding-edge
 // count and the energy gate (fitness rows, active flags).  Independent of heading offsets.
 void Evaluator::energyAndGate(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, double* d_fitness) {
@@ -666,7 +678,7 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
     PlanReduceArgs rd;
     rd.ids = d_ids; rd.offsets = d_offsets; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
     rd.active = d_active_; rd.rowmap = d_rowmap_; rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
-    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness;
+    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness; rd.partial = reducePartials(pop);
     groupBegin(KG_REDUCE);
     launch_plan_reduce(rd, numSMs_, stream_);
     groupEnd(KG_REDUCE);
@@ -793,7 +805,7 @@ void Evaluator::evaluatePopulationAngles(const int32_t* ids, const float* angles
     rd.ids = d_ids_; rd.offsets = d_offsets_; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
     rd.active = d_active_; rd.rowmap = d_rowmap_; rd.edgeRows = d_edgeRows_; rd.edgeOffsets = d_edgeOffsets_;
     rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
-    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness_;
+    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness_; rd.partial = reducePartials(pop);
     groupBegin(KG_REDUCE);
     launch_plan_reduce(rd, numSMs_, stream_);
     groupEnd(KG_REDUCE);
@@ -968,7 +980,7 @@ void Evaluator::renderKeysHeadingSearch(const int* d_keys, int nNew) {
         rd.ids = d_sortedKeys_; rd.offsets = d_pseudoOffsets_; rd.pop = C2; rd.N = N_; rd.hasStart = false; rd.loops = false;
         rd.active = d_pseudoActive_; rd.rowmap = d_rowmap_; rd.edgeRows = d_edgeRows_; rd.edgeOffsets = d_pseudoEdgeOffsets_;
         rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
-        rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_pseudoFitness_;
+        rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_pseudoFitness_; rd.partial = reducePartials(C2);
         launch_plan_reduce(rd, numSMs_, stream_);
         nLaunches_++;
         std::vector<double> fit((size_t)C2 * 4);

@@ -97,6 +97,7 @@ class Evaluator {
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
     void renderSnapshots(int nSnaps, int32_t* d_idImage);
     void requireQuickHeading() const;
+    double* reducePartials(int64_t pop);  // K6 scratch for populations too small to fill the GPU (nullptr otherwise)
     // postProcessing = true: both candidate headings of every key are rendered, the better one becomes the memo row
     void renderKeysHeadingSearch(const int* d_keys, int n);
     void decideHeadings(const std::vector<int>& keys);
@@ -160,6 +161,8 @@ class Evaluator {
     uint8_t* d_pseudoActive_ = nullptr;
     double* d_pseudoFitness_ = nullptr;
     int pseudoCap_ = 0;
+    double* d_partial_ = nullptr;
+    int64_t partialCap_ = 0;
     // shared rendering across ranks
     int* d_sortedKeys_ = nullptr;  // nKeys
     void* d_sortTmp_ = nullptr;

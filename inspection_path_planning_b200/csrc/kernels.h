@@ -41,14 +41,17 @@ struct PlanReduceArgs {
     bool hasStart, loops;
     const uint8_t* active;
     const int* rowmap;
-    const int* edgeRows = nullptr;         // optional ([id, angle] genes): row of edge e of plan p at edgeRows[edgeOffsets[p] + e],
-    const int64_t* edgeOffsets = nullptr;  // instead of rowmap[key]
     const uint32_t* rows;  // row pool
     int64_t rowWords;      // words per row (multiple of 4)
     const double* area;    // padded to nTiles * kTileTris
     int nTiles;
     double totalArea;
     double* fitness;
+    // optional scratch of pop * ceil(nTiles / 8) doubles: lets a very small population on a large mesh split the tiles of a plan over
+    // several CTAs (area sums per block of 8 tiles, added up in block order by a second kernel)
+    double* partial = nullptr;
+    const int* edgeRows = nullptr;         // optional ([id, angle] genes, heading search): row of edge e of plan p at
+    const int64_t* edgeOffsets = nullptr;  // edgeRows[edgeOffsets[p] + e] instead of rowmap[key]
 };
 
 // exact.cu (-fmad=false)
