@@ -39,7 +39,9 @@ class Parameters:
     PLAN_ORIGIN = None
     PLAN_LOOPS_AROUND = False
     HYPERVOLUME_REF_POINT = [1.01, 215]
-    SIMPLIFIED_VIEW_ANGLE = True
+    SIMPLIFIED_VIEW_ANGLE = True  # False: genes are [id, angleOffset] and the offsets are mutated too (mutateViewingAngles)
+    ANGLE_MUTATION_PROBABILITY = 0.01  # per waypoint
+    POLY_MUTATION_ETA = 20.0  # the reference uses an undefined POLY_MUTATION_ETA_PARAMETER (mutationAndRecombination.py:52); DEAP's usual value
     SENSOR_PARAMETERS = [2.0, 46.0, 46.0, 1024, 0.1, 10, 1, 1]
     USING_EDGE_MEMOISATION = True
 
@@ -62,8 +64,9 @@ class Individual(list):
         self.crowding_dist = 0.0
 
     @classmethod
-    def rand_init(cls, length, num_boxes, rng):
-        return cls([[rng.randrange(0, num_boxes)] for _ in range(length)])
+    def rand_init(cls, length, num_boxes, rng, with_angles=False):
+        """individuals.py:17-26: random viewpoints; with view angles every gene starts looking straight ahead ([id, 0])."""
+        return cls([[rng.randrange(0, num_boxes)] + ([0.0] if with_angles else []) for _ in range(length)])
 
     def clone(self):
         c = Individual([list(g) for g in self])
@@ -244,10 +247,42 @@ def clean_up_individual(ind):
         ind[:] = out
 
 
+def mut_polynomial_bounded(values, eta, low, up, indpb, rng):
+    """tools.mutPolynomialBounded (Deb's polynomial mutation as implemented in NSGA-II / DEAP), in place."""
+    for i, x in enumerate(values):
+        if rng.random() > indpb:
+            continue
+        delta_1 = (x - low) / (up - low)
+        delta_2 = (up - x) / (up - low)
+        rand = rng.random()
+        mut_pow = 1.0 / (eta + 1.0)
+        if rand < 0.5:
+            xy = 1.0 - delta_1
+            val = 2.0 * rand + (1.0 - 2.0 * rand) * xy ** (eta + 1.0)
+            delta_q = val ** mut_pow - 1.0
+        else:
+            xy = 1.0 - delta_2
+            val = 2.0 * (1.0 - rand) + 2.0 * (rand - 0.5) * xy ** (eta + 1.0)
+            delta_q = 1.0 - val ** mut_pow
+        values[i] = min(max(x + delta_q * (up - low), low), up)
+    return values
+
+
+def mutate_viewing_angles(ind, params, rng):
+    """:43-61 -- polynomial mutation of the angle offsets in [-1, 1] rad; True when something changed."""
+    angles = [g[1] for g in ind]
+    before = list(angles)
+    mut_polynomial_bounded(angles, params.POLY_MUTATION_ETA, -1.0, 1.0, params.ANGLE_MUTATION_PROBABILITY, rng)
+    for g, a in zip(ind, angles):
+        g[1] = a
+    return before != angles
+
+
 def mutate_waypoints(ind, num_boxes, params, rng):
     """:20-41 -- insert a random viewpoint at a random place, or delete one (never below MIN_PLAN_SIZE)."""
     if rng.random() < 0.5:
-        ind.insert(rng.randrange(len(ind) + 1), [rng.randrange(0, num_boxes)])
+        new_point = [rng.randrange(0, num_boxes)] + ([] if params.SIMPLIFIED_VIEW_ANGLE else [0.0])  # new points look straight ahead
+        ind.insert(rng.randrange(len(ind) + 1), new_point)
         return True
     if len(ind) > params.MIN_PLAN_SIZE:
         ind.pop(rng.randrange(len(ind)))
@@ -285,7 +320,8 @@ def initial_population(evaluator, params, seeds, num_boxes, max_energy, rng, sta
             pop.append(None)
             slots.append(len(pop) - 1)
     while slots:
-        cands = [Individual.rand_init(rng.randint(params.MIN_PLAN_SIZE, params.MAX_PLAN_SIZE), num_boxes, rng) for _ in slots]
+        cands = [Individual.rand_init(rng.randint(params.MIN_PLAN_SIZE, params.MAX_PLAN_SIZE), num_boxes, rng, not params.SIMPLIFIED_VIEW_ANGLE)
+                 for _ in slots]
         evaluate_batch(evaluator, cands, params, stats)
         left = []
         for s, c in zip(slots, cands):
@@ -307,7 +343,7 @@ def run_nsga2(evaluator, params, seed=None, use_seeds=True, log=None, on_generat
     seeds = []
     if use_seeds:
         for plan in evaluator.getSimplePlans():
-            seeds.append(Individual([[int(g[0])] for g in plan]))
+            seeds.append(Individual([[int(g[0])] + ([] if params.SIMPLIFIED_VIEW_ANGLE else [0.0]) for g in plan]))  # initializeFromList
         evaluate_batch(evaluator, seeds, params, stats)  # storeSeedFitnesses :35-43
     stats["seed_s"] = time.perf_counter() - t0
 
@@ -341,6 +377,10 @@ def run_nsga2(evaluator, params, seed=None, use_seeds=True, log=None, on_generat
                 if rng.random() <= params.WAYPOINT_MUTATION_PROBABILITY:
                     if mutate_waypoints(ind, num_boxes, params, rng):
                         ind.fitness = None
+        if (not params.SIMPLIFIED_VIEW_ANGLE) and params.ANGLE_MUTATION_PROBABILITY > 0:
+            for ind in offspring:
+                if mutate_viewing_angles(ind, params, rng):
+                    ind.fitness = None
         invalid = [ind for ind in offspring if ind.fitness is None]
         evaluate_batch(evaluator, invalid, params, stats)
         valid_offspring = [o for o in offspring if len(o) >= params.MIN_PLAN_SIZE]

@@ -180,3 +180,24 @@ def test_circling_plan_generator_stores_the_seed_plans_with_their_fitness(oracle
         assert tuple(ev.evaluatePlan(list(ind), False, 3, False)) == pytest.approx(ind.fitness)
     d = oc.load_dumped_population(str(tmp_path / "populations" / "circling_plans.yml"))
     assert len(d["population"]) == len(inds) and d["pareto_front"] is None and d["scene"] == "sphere.obj"
+
+
+def test_polynomial_mutation_stays_in_bounds_and_moves_values():
+    rng = random.Random(5)
+    vals = [0.0, 0.9, -0.95, 0.3] * 50
+    out = oc.mut_polynomial_bounded(list(vals), 20.0, -1.0, 1.0, 1.0, rng)
+    assert all(-1.0 <= v <= 1.0 for v in out) and sum(a != b for a, b in zip(out, vals)) > 150
+    assert max(abs(a - b) for a, b in zip(out, vals)) < 1.0  # eta = 20: small moves
+    assert oc.mut_polynomial_bounded(list(vals), 20.0, -1.0, 1.0, 0.0, rng) == vals
+
+
+def test_generational_loop_with_view_angle_genes(oracle_mod):
+    sp = list(oc.Parameters.SENSOR_PARAMETERS)
+    sp[3] = 48
+    params = oc.Parameters(NUM_INDIVS=12, NUM_GENERATIONS=3, SENSOR_PARAMETERS=sp, SIMPLIFIED_VIEW_ANGLE=False, ANGLE_MUTATION_PROBABILITY=0.3)
+    ev = oracle_mod.Oracle(mesh_path("sphere"), sp)
+    pop, pf, logbook, stats = oc.run_nsga2(ev, params, seed=3)
+    assert all(len(g) == 2 and -1.0 <= g[1] <= 1.0 for ind in pop for g in ind)
+    assert any(g[1] != 0.0 for ind in pop for g in ind)  # offsets were mutated and kept
+    for ind in pop[:4]:
+        assert tuple(ev.evaluatePlan(list(ind), True, 3, False)) == pytest.approx(ind.fitness)
