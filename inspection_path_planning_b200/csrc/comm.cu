@@ -156,31 +156,36 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
         c->offCap = mine + mine / 4 + 16;
         IPP_CUDA_CHECK(cudaMalloc(&c->d_offsets, (size_t)c->offCap * sizeof(int64_t)));
     }
-    // The edges of the WHOLE population are rendered once across the ranks and exchanged (second exchange step of this path: the
-    // fresh bitmap rows), so that a rank does not render an edge its shard shares with another rank's shard.
-    // (memoization == false keeps the reference's meaning -- nothing rendered for this call is remembered -- and renders per shard)
-    if (c->world > 1 && pop > 0 && c->shareEdges && memo) {
-        const int64_t allGenes = offsets[pop];
-        if (allGenes + 1 > c->allIdsCap) {
-            cudaFree(c->d_allIds);
-            c->allIdsCap = allGenes + allGenes / 4 + 16;
-            IPP_CUDA_CHECK(cudaMalloc(&c->d_allIds, (size_t)c->allIdsCap * sizeof(int32_t)));
-        }
-        if (pop + 2 > c->allOffCap) {
-            cudaFree(c->d_allOffsets);
-            c->allOffCap = pop + pop / 4 + 16;
-            IPP_CUDA_CHECK(cudaMalloc(&c->d_allOffsets, (size_t)c->allOffCap * sizeof(int64_t)));
-        }
-        IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_allIds, ids, (size_t)allGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_allOffsets, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        NcclCollectives cx(c);
-        ev.renderEdgesShared(c->d_allIds, c->d_allOffsets, pop, noLimit, cx);
-    }
     std::vector<int64_t> off((size_t)mine + 1);
     for (int64_t i = 0; i <= mine; ++i) off[i] = offsets[lo + i] - g0;
     if (mine > 0) {
         IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_ids, ids + g0, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_offsets, off.data(), (size_t)(mine + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    // The edges of the WHOLE population are rendered once across the ranks and exchanged (second exchange step of this path: the
+    // fresh bitmap rows), so that a rank does not render an edge its shard shares with another rank's shard.  Skipped when no
+    // shard uses an edge its rank has not got: the steady state of a memoised run costs one probe kernel and one all-reduce.
+    // (memoization == false keeps the reference's meaning -- nothing rendered for this call is remembered -- and renders per shard)
+    if (c->world > 1 && pop > 0 && c->shareEdges && memo) {
+        double unseen = (double)ev.countUnseenEdges(c->d_ids, c->d_offsets, mine, noLimit);
+        comm_allreduce(c, &unseen, 1, 1, st);
+        if (unseen > 0) {
+            const int64_t allGenes = offsets[pop];
+            if (allGenes + 1 > c->allIdsCap) {
+                cudaFree(c->d_allIds);
+                c->allIdsCap = allGenes + allGenes / 4 + 16;
+                IPP_CUDA_CHECK(cudaMalloc(&c->d_allIds, (size_t)c->allIdsCap * sizeof(int32_t)));
+            }
+            if (pop + 2 > c->allOffCap) {
+                cudaFree(c->d_allOffsets);
+                c->allOffCap = pop + pop / 4 + 16;
+                IPP_CUDA_CHECK(cudaMalloc(&c->d_allOffsets, (size_t)c->allOffCap * sizeof(int64_t)));
+            }
+            IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_allIds, ids, (size_t)allGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_allOffsets, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            NcclCollectives cx(c);
+            ev.renderEdgesShared(c->d_allIds, c->d_allOffsets, pop, noLimit, cx);
+        }
     }
     comm_eval_device_and_allgather(ev, c->d_ids, nullptr, c->d_offsets, mine, nGenes, per, memo, noLimit, c->d_gather);
     IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, c->d_gather, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -489,6 +489,27 @@ void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles, b
     if (publish) liveRows_ += nNew;
 }
 
+int64_t Evaluator::countUnseenEdges(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit) {
+    bind();
+    if (pop <= 0) return 0;
+    if (pop > sharedCap_) {
+        cudaFree(d_activeShared_);
+        cudaFree(d_fitShared_);
+        sharedCap_ = pop + pop / 4 + 16;
+        d_activeShared_ = dalloc<uint8_t>(sharedCap_);
+        d_fitShared_ = dalloc<double>(sharedCap_ * 4);
+    }
+    energyAndGate(d_ids, d_offsets, pop, noLimit, d_fitShared_);  // (active flags land in d_active_)
+    PlanMarkArgs mk;
+    mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
+    mk.active = d_active_; mk.coll = nullptr; mk.rowmap = d_rowmap_; mk.used = nullptr; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
+    mk.errFlag = d_scalars_ + 3;
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+    launch_probe_rows(mk, stream_);
+    nLaunches_++;
+    return readInt(d_scalars_);
+}
+
 int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx) {
     bind();
     if (pop <= 0) return 0;

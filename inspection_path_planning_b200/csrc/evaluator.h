@@ -46,6 +46,8 @@ class Evaluator {
     // Multi-GPU: the edges the WHOLE population needs are rendered once across the ranks (contiguous chunks of the sorted new
     // keys), the fresh bitmap rows are all-gathered, and every rank's memo ends up complete.  Every rank must pass the same
     // population and hold the same memo contents (checked).  Returns the number of edges this rank rendered itself.
+    // number of edge uses of this (device-resident) population whose bitmap the memo does not hold yet (energy gate applied)
+    int64_t countUnseenEdges(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit);
     int64_t renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx);
     int64_t updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
     int64_t memoSize() const { return liveRows_ + (int64_t)angleMemo_.size(); }

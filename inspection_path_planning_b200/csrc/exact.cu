@@ -435,11 +435,30 @@ __global__ void k_mark_rows(PlanMarkArgs a) {
     }
 }
 
+__global__ void k_probe_rows(PlanMarkArgs a) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= a.pop) return;
+    if (a.active && !a.active[p]) return;
+    PlanIter it{a.ids, a.offsets[p], a.offsets[p + 1], a.N, a.hasStart, a.loops, 0};
+    int m = it.count();
+    int prev = m > 0 ? it.at(0) : 0;
+    int unseen = 0;
+    for (int k = 1; k < m; ++k) {
+        int cur = it.at(k);
+        if (a.rowmap[prev * a.N + cur] == -1) unseen++;
+        prev = cur;
+    }
+    if (unseen) atomicAdd(a.newCount, unseen);
+}
+
 void launch_mark_collisions(const PlanMarkArgs& a, cudaStream_t st) {
     if (a.pop > 0) k_mark_collisions<<<(unsigned)((a.pop + 127) / 128), 128, 0, st>>>(a);
 }
 void launch_energy(const PlanEnergyArgs& a, cudaStream_t st) {
     if (a.pop > 0) k_energy<<<(unsigned)((a.pop + 127) / 128), 128, 0, st>>>(a);
+}
+void launch_probe_rows(const PlanMarkArgs& a, cudaStream_t st) {
+    if (a.pop > 0) k_probe_rows<<<(unsigned)((a.pop + 127) / 128), 128, 0, st>>>(a);
 }
 void launch_mark_rows(const PlanMarkArgs& a, cudaStream_t st) {
     if (a.pop > 0) k_mark_rows<<<(unsigned)((a.pop + 127) / 128), 128, 0, st>>>(a);

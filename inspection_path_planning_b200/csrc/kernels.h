@@ -68,6 +68,8 @@ void launch_single_snapshot(Snapshot* d_snap, const double eye[3], const double 
 void launch_mark_collisions(const PlanMarkArgs& a, cudaStream_t st);
 void launch_energy(const PlanEnergyArgs& a, cudaStream_t st);
 void launch_mark_rows(const PlanMarkArgs& a, cudaStream_t st);
+// counts (into a.newCount) the edges of the active plans that have no bitmap row yet, without claiming them
+void launch_probe_rows(const PlanMarkArgs& a, cudaStream_t st);
 void launch_gc_rows(int* d_rowmap, const uint8_t* d_used, int nKeys, int* d_freeStack, int* d_freeTop, int* d_live, cudaStream_t st);
 void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, cudaStream_t st);
 void launch_publish_rows(const int* d_keys, const int* d_rows, int n, int* d_rowmap, cudaStream_t st);
