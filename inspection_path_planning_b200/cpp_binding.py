@@ -13,6 +13,7 @@ Differences from the SWIG build, all deliberate:
   * the GL viewers (how_to_plot != nothing, storePlanImage, viewMatrixSelector) are out of scope and raise.
 """
 import ctypes as C
+import itertools
 import os
 
 import numpy as np
@@ -50,29 +51,57 @@ def pack_population(plans, with_angles=False):
     None when every offset is zero -- the straight-ahead heading evaluates like [id] and shares its memo.
     Gene -> id uses the reference's rounding `(size_t)(gene + 0.5)` (PlanInterpreterBoxOrder.cpp:280)."""
     offsets = np.zeros(len(plans) + 1, dtype=np.int64)
-    flat, ang = [], []
-    for i, p in enumerate(plans):
-        for g in p:
-            a = 0.0
-            if isinstance(g, (list, tuple, np.ndarray)):
-                if len(g) == 2:
-                    a = float(g[1])
-                elif len(g) != 1:
-                    raise ValueError("a gene is [id] or [id, angleOffset]")
-                g = g[0]
-            flat.append(g)
-            ang.append(a)
-        offsets[i + 1] = len(flat)
+    offsets[1:] = np.cumsum(np.fromiter((len(p) for p in plans), dtype=np.int64, count=len(plans)))
+    flat = ang = None
+    try:
+        # fast path (C-level loops): bare ids, or genes that are all sequences of length 1 or 2
+        genes = list(itertools.chain.from_iterable(plans))
+        if not genes:
+            flat, ang = np.zeros(0), np.zeros(0)
+        elif isinstance(genes[0], (list, tuple, np.ndarray)):
+            lens = set(map(len, genes))
+            if lens <= {1, 2}:
+                flat = np.fromiter((g[0] for g in genes), dtype=np.float64, count=len(genes))
+                ang = np.zeros(len(genes)) if lens == {1} else np.fromiter((g[1] if len(g) == 2 else 0.0 for g in genes), dtype=np.float64,
+                                                                          count=len(genes))
+            else:
+                raise ValueError("a gene is [id] or [id, angleOffset]")
+        else:
+            try:
+                flat = np.asarray(genes, dtype=np.float64)
+            except ValueError:  # bare ids mixed with sequences
+                flat = None
+            if flat is not None and flat.ndim != 1:
+                flat = None
+            if flat is not None:
+                ang = np.zeros(flat.size)
+    except TypeError:
+        flat = ang = None
+    if flat is None:  # mixed gene shapes: gene by gene
+        flat, ang = [], []
+        for p in plans:
+            for g in p:
+                a = 0.0
+                if isinstance(g, (list, tuple, np.ndarray)):
+                    if len(g) == 2:
+                        a = float(g[1])
+                    elif len(g) != 1:
+                        raise ValueError("a gene is [id] or [id, angleOffset]")
+                    g = g[0]
+                flat.append(g)
+                ang.append(a)
+        ang = np.asarray(ang, dtype=np.float64)
     vals = np.asarray(flat, dtype=np.float64)
     ids = np.trunc(vals + 0.5)
     ids[vals + 0.5 < 0] = 0.0  # a negative gene (the -1 cells of the seed plans) truncates to 0 like the reference
     ids = np.ascontiguousarray(ids.astype(np.int32))
+    has_angles = bool(np.any(ang != 0.0))
     if not with_angles:
-        if any(a != 0.0 for a in ang):
+        if has_angles:
             raise NotImplementedError("[id, angle] genes with a non-zero offset need the host-pointer evaluation calls (evaluatePlan, "
                                       "evaluatePopulation, updateMemoisedEdges)")
         return ids, offsets
-    angles = np.ascontiguousarray(np.asarray(ang, dtype=np.float32)) if any(a != 0.0 for a in ang) else None
+    angles = np.ascontiguousarray(ang.astype(np.float32)) if has_angles else None
     return ids, angles, offsets
 
 
