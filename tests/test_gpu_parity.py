@@ -712,3 +712,24 @@ def test_tiny_meshes_one_triangle_and_a_twelve_triangle_box(oracle_mod, tmp_path
                 _compare_population(g, o, plans, memo=True, no_limit=True)
         finally:
             g.close()
+
+
+def test_edge_cache_full_is_reported_and_recoverable(monkeypatch):
+    """A row pool too small for a population (IPP_CACHE_GB) raises instead of overwriting rows; updateMemoisedEdges makes room."""
+    from inspection_path_planning_b200 import cpp_binding
+    monkeypatch.setenv("IPP_CACHE_GB", "0.000004")  # ~4 kB: a few rows of the 960-triangle sphere
+    g = cpp_binding.PlanCoverageEstimator(mesh_path("sphere"), specs(32))
+    try:
+        rng = np.random.default_rng(7)
+        plans = random_plans(rng, g.getNumberOfBoxes(), 30, 6)
+        with pytest.raises(RuntimeError, match="cache full"):
+            g.evaluatePopulation(plans, True, True)
+        small = [plans[0][:3]]
+        a = g.evaluatePopulation(small, True, True)
+        assert g.updateMemoisedEdges([]) == 0 and g.memo_size() == 0
+        b = g.evaluatePopulation(small, True, True)
+        assert np.array_equal(a, b)
+        with pytest.raises(IndexError):
+            g.evaluatePopulation([[[0], [g.getNumberOfBoxes()]]], True, True)
+    finally:
+        g.close()
