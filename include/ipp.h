@@ -155,8 +155,11 @@ int ipp_flush_l2(ipp_t* h);
 int ipp_counters(ipp_t* h, int64_t* out8, int reset);
 /* statistics of the edge-visibility kernel since the last reset (reset by ipp_counters too):
  * [0] acceleration-structure data fetched in 64-byte units (BVH nodes of the tile-walking variant, 8 leaf-bin entries of the
- * binned variant), [1] triangles staged (48 B each), [2] 32x32-pixel tiles rasterised, [3] pixel-centre rays */
-int ipp_visibility_stats(ipp_t* h, int64_t* out4, int reset);
+ * binned variant), [1] triangles staged (48 B each), [2] 32x32-pixel tiles rasterised, [3] pixel-centre rays, and, only when the
+ * library was built with -DIPP_VIS_DIAG (they cost 2 % of the kernel; 0 otherwise), for the binned variant [4] staged triangles that
+ * survived set-up (can produce a fragment in their tile), [5] tiles in which some ray never hit, so that the leaf list was walked
+ * to its end */
+int ipp_visibility_stats(ipp_t* h, int64_t* out6, int reset);
 /* which edge-visibility kernel renders the item buffers: 1 = depth-sorted leaf bins per 128x128 supertile (the default when the
  * mesh has <= 16384 BVH leaves and the image is <= 1024 pixels a side), 0 = BVH frustum walk per tile.  Same sampling rule and
  * rasteriser either way.  *out_active (nullable) receives the variant in force after the call; use_bins < 0 only queries. */

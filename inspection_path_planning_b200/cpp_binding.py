@@ -355,9 +355,9 @@ class PlanCoverageEstimator(object):
         return dict(zip(keys, (int(x) for x in out)))
 
     def visibility_stats(self, reset=False):
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(6, dtype=np.int64)
         _lib.check(self._L.ipp_visibility_stats(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
-        return dict(zip(["nodes", "triangles", "tiles", "rays"], (int(x) for x in out)))
+        return dict(zip(["nodes", "triangles", "tiles", "rays", "live_triangles", "open_tiles"], (int(x) for x in out)))
 
     def visibility_variant(self, use_bins=None):
         """Selects (True / False) or queries (None) the edge-visibility kernel: leaf bins or BVH walk per tile."""

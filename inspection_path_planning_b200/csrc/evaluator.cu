@@ -300,13 +300,14 @@ void Evaluator::counters(int64_t out[8], bool reset) {
         IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
     }
 }
-void Evaluator::visibilityStats(int64_t out[4], bool reset) {
+void Evaluator::visibilityStats(int64_t out[6], bool reset) {
     bind();
     unsigned long long c[8];
     IPP_CUDA_CHECK(cudaMemcpyAsync(c, d_visCounters_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
     sync();
     // out[0]: 64-byte units of acceleration-structure data fetched = BVH nodes (visibility.cu) + 8-byte bin entries / 8 (visibility_bins.cu)
     out[0] = (int64_t)c[2] + (int64_t)(c[5] / 8); out[1] = (int64_t)c[3]; out[2] = (int64_t)c[4]; out[3] = (int64_t)c[0];
+    out[4] = (int64_t)c[6]; out[5] = (int64_t)c[7];  // binned variant only
     if (reset) IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
 }
 void Evaluator::timerStart() {

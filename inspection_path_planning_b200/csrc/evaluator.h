@@ -69,7 +69,7 @@ class Evaluator {
     double timerStop();
     void flushL2();
     void counters(int64_t out[8], bool reset);
-    void visibilityStats(int64_t out[4], bool reset);
+    void visibilityStats(int64_t out[6], bool reset);
     void kernelTime(int which, double* ms, int64_t* launches, bool reset);
     void setProfiling(bool on) { profiling_ = on; }
     bool usesBins() const { return useBins_; }

@@ -268,9 +268,9 @@ int ipp_counters(ipp_t* h, int64_t* out8, int reset) {
     E(h).counters(out8, reset != 0);
     IPP_CATCH
 }
-int ipp_visibility_stats(ipp_t* h, int64_t* out4, int reset) {
+int ipp_visibility_stats(ipp_t* h, int64_t* out6, int reset) {
     IPP_TRY
-    E(h).visibilityStats(out4, reset != 0);
+    E(h).visibilityStats(out6, reset != 0);
     IPP_CATCH
 }
 int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,

@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
 // ---------------------------------------------------------------------------------------------------------------------
 // K4b
 // ---------------------------------------------------------------------------------------------------------------------
+#ifdef IPP_VIS_DIAG
+__device__ unsigned long long g_diag[1];  // diagnostic build: triangles staged in tiles that stayed open
+#endif
 __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
                                                                  const int* __restrict__ superOffset, int nSnaps,
                                                                  const unsigned long long* __restrict__ table, int stride,
@@ -199,6 +202,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     unsigned long long* list = scratch + (size_t)(blockIdx.x * kBinWarps + warp) * stride;
     unsigned long long myRays = 0, myEntries = 0;
     unsigned myTris = 0, myTiles = 0;  // statistics (lane 0 only matters)
+#ifdef IPP_VIS_DIAG
+    unsigned myLive = 0, myOpen = 0, myOpenTris = 0;
+#endif
     const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
     const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
     const float zNear = cam.zNear, zFar = cam.zFar;
@@ -260,6 +266,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
             TileGeom tg;
             tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
             bool inited = false, tileHit = false;
+#ifdef IPP_VIS_DIAG
+            const unsigned trisBefore = myTris;
+#endif
             // Triangles wait in lane order: lanes < pend carry one each (myTri, its leaf's depth myZ) from the previous chunk.
             int pend = 0, myTri = 0;
             float myZ = 0.f;
@@ -269,6 +278,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                 bool mineOk = false;
                 if (mineValid) mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
                 const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
+#ifdef IPP_VIS_DIAG
+                myLive += __popc(live);
+#endif
                 if (live) {
                     if (!inited) {
                         tile_init(S.t, S.id, lane, vw, vh, zFar);
@@ -339,6 +351,12 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
             if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
             myRays += (unsigned long long)(vw * vh);
             myTiles++;
+#ifdef IPP_VIS_DIAG
+            if (zcull == zFar * kDepthTie) {  // some ray of the tile never hit: the list was walked to its end
+                myOpen++;
+                myOpenTris += myTris - trisBefore;
+            }
+#endif
             __syncwarp();
         }
     }
@@ -347,6 +365,11 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         atomicAdd(&counters[3], (unsigned long long)myTris);
         atomicAdd(&counters[4], (unsigned long long)myTiles);
         atomicAdd(&counters[5], myEntries);
+#ifdef IPP_VIS_DIAG
+        atomicAdd(&counters[6], (unsigned long long)myLive);
+        atomicAdd(&counters[7], (unsigned long long)myOpen);
+        atomicAdd(&g_diag[0], (unsigned long long)myOpenTris);
+#endif
     }
 }
 
@@ -412,6 +435,12 @@ void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, cons
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
     k_visibility_bins<<<grid, kBinThreads, 0, st>>>(sc, cam, d_snaps, d_superOffset, nSnaps, b.table, b.stride, b.tableCount, b.tileMask,
                                                    b.superMask, b.scratch, d_flags, d_idImage, d_counters);
+#ifdef IPP_VIS_DIAG
+    unsigned long long d[1];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(d, g_diag, sizeof(d));
+    fprintf(stderr, "[vis diag, cumulative] triangles staged in open tiles %llu\n", d[0]);
+#endif
 }
 
 }  // namespace ipp

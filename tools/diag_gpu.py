@@ -34,6 +34,9 @@ for it in range(3):
     vs = g.visibility_stats()
     if vs["tiles"]:
         print("   per tile: nodes %.1f triangles %.1f (tiles %d)" % (vs["nodes"] / vs["tiles"], vs["triangles"] / vs["tiles"], vs["tiles"]), flush=True)
+        if vs["live_triangles"]:  # library built with -DIPP_VIS_DIAG
+            print("   per tile: triangles surviving set-up %.1f, %.1f %% of the tiles stay open" % (
+                vs["live_triangles"] / vs["tiles"], 100.0 * vs["open_tiles"] / vs["tiles"]), flush=True)
     kt = {names[k]: g.kernel_time(k) for k in range(6)}
     print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  counters %s" % (it, dt, pop / dt, (1 - fit[:, 0]).mean(), c), flush=True)
     print("   kernel ms:", {k: (round(v[0], 3), v[1]) for k, v in kt.items()}, flush=True)
