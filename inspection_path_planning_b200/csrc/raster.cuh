@@ -151,7 +151,13 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
         const float ca = __fmaf_rn(eas, eas >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(eau, eau >= 0.f ? g.bYmax : g.bYmin, eaf));
         const float cb = __fmaf_rn(ebs, ebs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(ebu, ebu >= 0.f ? g.bYmax : g.bYmin, ebf));
         const float cc = __fmaf_rn(ecs, ecs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(ecu, ecu >= 0.f ? g.bYmax : g.bYmin, ecf));
-        unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && zloTri <= bz);
+        // nearest depth the triangle's plane can have inside block b: depth = vol / det and det is linear, so its largest value over
+        // the block sits at an extreme pixel centre; pushed up by a bound on its rounding error (|X|, |Y| < 1) and compared with a
+        // relative margin far above that of the per-pixel depth.  det <= 0 everywhere: no ray of the block meets the front of the plane.
+        const float dmax = __fmaf_rn(gs, gs >= 0.f ? g.bXmax : g.bXmin, __fmaf_rn(gu, gu >= 0.f ? g.bYmax : g.bYmin, gf)) +
+                           2e-6f * (fabsf(gs) + fabsf(gu) + fabsf(gf));
+        const float zloBlk = fmaxf(zloTri, vol * rcp_approx(dmax) * 0.9999f);
+        unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && dmax > 0.f && zloBlk <= bz);
         // kBlocksPerStep blocks per step: their tests are independent (different pixels), which hides the latency of one behind
         // the others
         while (todo) {
