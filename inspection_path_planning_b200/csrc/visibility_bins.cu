@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
                 cxs[c] = ((c & 1) ? xx1 : xx0) + ((c & 2) ? xy1 : xy0) + ((c & 4) ? xz1 : xz0);
                 cys[c] = ((c & 1) ? yx1 : yx0) + ((c & 2) ? yy1 : yy0) + ((c & 4) ? yz1 : yz0);
                 if (czs[c] >= zClip) {
-                    const float iz = 1.f / czs[c];
+                    const float iz = rcp_approx(czs[c]);  // czs >= zClip >= 0.01; the rectangle is widened by a pixel below
                     const float X = cxs[c] * iz, Y = cys[c] * iz;
                     Xmin = fminf(Xmin, X); Xmax = fmaxf(Xmax, X);
                     Ymin = fminf(Ymin, Y); Ymax = fmaxf(Ymax, Y);
@@ -152,6 +152,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
     }
     if (mine) atomicAdd(&nValid, mine);
     __syncthreads();
+    if (nValid == 0) {  // nothing of the scene in this view: no sort
+        if (tid < 32) tileMask[(size_t)si * 32 + tid] = 0u;
+        if (tid == 0) { tableCount[si] = 0; superMask[si] = 0ull; nSuper[si] = 0; }
+        return;
+    }
     unsigned long long keys[ITEMS];
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) keys[it] = stage[it * THREADS + tid];
