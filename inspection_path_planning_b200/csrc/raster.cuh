@@ -171,7 +171,7 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
             }
             float tt[kBlocksPerStep], ht[kBlocksPerStep];
             bool in[kBlocksPerStep];
-            int idx[kBlocksPerStep];
+            int idx[kBlocksPerStep], hid[kBlocksPerStep];
 #pragma unroll
             for (int u = 0; u < kBlocksPerStep; ++u) {
                 const float X = __fmaf_rn((float)(blk[u] & 3), g.kx8, g.Xl), Y = __fmaf_rn((float)(blk[u] >> 2), g.ky4, g.Yl);
@@ -181,13 +181,13 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
                 tt[u] = vol * rcp_approx(gs * X + (gu * Y + gf));    // det == 0: inf / NaN fails the range test
                 idx[u] = blk[u] * 32 + lane;
                 ht[u] = St[idx[u]];
+                hid[u] = Sid[idx[u]];  // read with the depth, not after the depth test: one shared-memory round trip per step
             }
 #pragma unroll
             for (int u = 0; u < kBlocksPerStep; ++u) {
                 // depth-tie band: fragments within a relative 2^-16 of the nearest are ties and the lowest id wins
                 if (in[u] && tt[u] >= zNear && tt[u] <= zFar && tt[u] <= ht[u] * kDepthTie) {
-                    const int hid = Sid[idx[u]];
-                    Sid[idx[u]] = (tt[u] * kDepthTie < ht[u]) ? id : min(hid, id);  // clearly nearer: replace; inside the band: lowest id
+                    Sid[idx[u]] = (tt[u] * kDepthTie < ht[u]) ? id : min(hid[u], id);  // clearly nearer: replace; inside the band: lowest id
                     St[idx[u]] = fminf(ht[u], tt[u]);
                     dirty = true;
                 }

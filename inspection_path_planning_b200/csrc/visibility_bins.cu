@@ -29,6 +29,10 @@ constexpr int kBinWarps = 4;
 constexpr int kBinThreads = kBinWarps * 32;
 constexpr unsigned long long kNoEntry = ~0ull;
 constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
+#ifndef IPP_FILTER_UNROLL
+#define IPP_FILTER_UNROLL 4
+#endif
+constexpr int kFilterUnroll = IPP_FILTER_UNROLL;    // table loads a lane keeps in flight while a supertile's list is filtered
 
 struct BinShared {
     float t[kTilePixels];
@@ -244,15 +248,24 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         const int nEnt = __ldg(tableCount + si);
         const unsigned long long* tab = table + (size_t)si * stride;
         int L = 0;
-        for (int base = 0; base < nEnt; base += 32) {
-            const int i = base + lane;
-            const unsigned long long e = i < nEnt ? __ldg(tab + i) : 0ull;
-            const unsigned r = (unsigned)(e >> 28);
-            const unsigned tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
-            const bool ok = i < nEnt && (tx0 >> 2) <= ssx && (tx1 >> 2) >= ssx && (ty0 >> 2) <= ssy && (ty1 >> 2) >= ssy;
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) list[L + __popc(m & ltMask)] = e;
-            L += __popc(m);
+        for (int base = 0; base < nEnt; base += 32 * kFilterUnroll) {  // kFilterUnroll loads in flight per lane
+            unsigned long long ev[kFilterUnroll];
+#pragma unroll
+            for (int u = 0; u < kFilterUnroll; ++u) {
+                const int i = base + 32 * u + lane;
+                ev[u] = i < nEnt ? __ldg(tab + i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kFilterUnroll; ++u) {
+                const int i = base + 32 * u + lane;
+                const unsigned long long e = ev[u];
+                const unsigned r = (unsigned)(e >> 28);
+                const unsigned tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
+                const bool ok = i < nEnt && (tx0 >> 2) <= ssx && (tx1 >> 2) >= ssx && (ty0 >> 2) <= ssy && (ty1 >> 2) >= ssy;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) list[L + __popc(m & ltMask)] = e;
+                L += __popc(m);
+            }
         }
         myEntries += (unsigned long long)nEnt;
         __syncwarp();
