@@ -215,7 +215,7 @@ Evaluator::~Evaluator() {
     cudaFree(d_snaps_); cudaFree(d_ntiles_); cudaFree(d_tileOffset_); cudaFree(d_scanTmp_);
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
     cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
-    cudaFree(bins_.scratch); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
+    cudaFree(bins_.scratch); cudaFree(bins_.records); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
     cudaFree(d_partial_);
     cudaFree(d_pseudoOffsets_); cudaFree(d_pseudoEdgeOffsets_); cudaFree(d_pseudoActive_); cudaFree(d_pseudoFitness_);
     cudaFree(d_angleBuf_); cudaFree(d_edgeRows_); cudaFree(d_edgeOffsets_); cudaFree(d_rowList_);
@@ -379,6 +379,8 @@ void Evaluator::ensureSnapBuffers(int64_t nSnaps) {
     }
     if (useBins_ && !bins_.scratch)
         bins_.scratch = dalloc<unsigned long long>((size_t)bins_.gridBlocks * bins_warps_per_block() * bins_.stride);
+    if (useBins_ && !bins_.records)
+        bins_.records = reinterpret_cast<float4*>(dalloc<float>((size_t)bins_.gridBlocks * bins_warps_per_block() * bins_record_floats_per_warp()));
 }
 
 void Evaluator::setUseBins(bool on) {

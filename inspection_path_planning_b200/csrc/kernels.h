@@ -104,11 +104,13 @@ struct BinBuffers {
     unsigned long long* superMask = nullptr;  // [poses] occupied 128x128 supertiles (bit = sy * 8 + sx)
     int* nSuper = nullptr;                    // [poses + 1] popcount of superMask
     unsigned long long* scratch = nullptr;    // [gridBlocks * warps][stride] per-warp supertile lists
+    float4* records = nullptr;                // [gridBlocks * warps][bins_record_floats_per_warp() / 4] set-up triangles of a supertile
     int stride = 0, gridBlocks = 0;
 };
 bool bins_supported(const DeviceScene& sc, const CameraParams& cam);
 int bins_grid_blocks();
 int bins_warps_per_block();
+size_t bins_record_floats_per_warp();
 int bins_table_stride(int nLeaves);
 void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, int nSnaps, const BinBuffers& b,
                        cudaStream_t st);

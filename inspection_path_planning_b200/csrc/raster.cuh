@@ -85,8 +85,11 @@ __device__ __forceinline__ void tile_init(float* __restrict__ St, int* __restric
 // >= 0 and det > 0.  Setup runs in fp64 from the exact fp32 vertices, the fp32 eye and the fp64 camera basis; only the final
 // coefficients are rounded to fp32 (in fp32 the normal of an edge that points at the camera, |A' x e| << |A'||e|, lost up to
 // 0.03 pixel).
-__device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
-                                               float oy, float oz, float zNear, float zcull, const TileGeom& g) {
+// kPoseOnly: the part that does not depend on the tile -- zcull is then the far bound of the pose, [14] receives the nearest vertex
+// depth itself and the tile test is left to stage_record() below, which repeats it with the same expressions.
+template <bool kPoseOnly>
+__device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
+                                                 float oy, float oz, float zNear, float zcull, const TileGeom& g) {
     const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
     float valid = -1.f;
     if (b.w == 0.f) {  // not degenerate
@@ -118,15 +121,42 @@ __device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snap
             o[9] = sg * (float)ddot(ngx, ngy, ngz, fX, fY, fZ); o[10] = sg * (float)ddot(ngx, ngy, ngz, sX, sY, sZ); o[11] = sg * (float)ddot(ngx, ngy, ngz, uX, uY, uZ);
             o[12] = sg * (float)vol;
             o[13] = a.w;  // triangle id (int bits)
+            if constexpr (kPoseOnly) {
+                o[14] = zlo;
+            } else {
             // can any pixel centre of the tile be inside?  Each edge function is monotone in X and in Y (also as computed), so its
             // value at the extreme pixel centre of the tile bounds it over the tile.
             const float ma = __fmaf_rn(o[1], o[1] >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(o[2], o[2] >= 0.f ? g.tYmax : g.tYmin, o[0]));
             const float mb = __fmaf_rn(o[4], o[4] >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(o[5], o[5] >= 0.f ? g.tYmax : g.tYmin, o[3]));
             const float mc = __fmaf_rn(o[7], o[7] >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(o[8], o[8] >= 0.f ? g.tYmax : g.tYmin, o[6]));
             if (fminf(fminf(ma, mb), mc) < 0.f) valid = -1.f;
+            }
         }
     }
     o[15] = valid;
+    return valid >= 0.f;
+}
+__device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
+                                               float oy, float oz, float zNear, float zcull, const TileGeom& g) {
+    return setup_triangle_t<false>(sc, sp, tri, o, ox, oy, oz, zNear, zcull, g);
+}
+
+// The tile's half of the set-up for a triangle whose pose half (setup_triangle_t<true>) sits in a 64-byte record r: the depth test
+// against the tile's farthest hit and the tile-level edge test, then the staged copy in shared memory.  Same expressions, same
+// bits as setup_triangle().  r was written by this warp earlier in the same kernel: plain loads.
+__device__ __forceinline__ bool stage_record(const float4* r, float* __restrict__ o, float zcull, const TileGeom& g) {
+    const float4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
+    float valid = q3.w;
+    if (valid >= 0.f && q3.z <= zcull * 1.000001f) {
+        const float ma = __fmaf_rn(q0.y, q0.y >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(q0.z, q0.z >= 0.f ? g.tYmax : g.tYmin, q0.x));
+        const float mb = __fmaf_rn(q1.x, q1.x >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(q1.y, q1.y >= 0.f ? g.tYmax : g.tYmin, q0.w));
+        const float mc = __fmaf_rn(q1.w, q1.w >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(q2.x, q2.x >= 0.f ? g.tYmax : g.tYmin, q1.z));
+        if (fminf(fminf(ma, mb), mc) < 0.f) valid = -1.f;
+    } else {
+        valid = -1.f;
+    }
+    float4* o4 = reinterpret_cast<float4*>(o);
+    o4[0] = q0; o4[1] = q1; o4[2] = q2; o4[3] = make_float4(q3.x, q3.y, q3.z, valid);
     return valid >= 0.f;
 }
 

@@ -29,12 +29,13 @@ constexpr int kBinWarps = 4;
 constexpr int kBinThreads = kBinWarps * 32;
 constexpr unsigned long long kNoEntry = ~0ull;
 constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
+constexpr int kBinRecords = 4096;   // set-up triangles (64 B each) a warp can keep for one supertile
 #ifndef IPP_FILTER_UNROLL
 #define IPP_FILTER_UNROLL 4
 #endif
 constexpr int kFilterUnroll = IPP_FILTER_UNROLL;    // table loads a lane keeps in flight while a supertile's list is filtered
 
-struct BinShared {
+struct __align__(16) BinShared {
     float t[kTilePixels];
     int id[kTilePixels];
     float tri[kPending][kTriWords];
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                                                                  const unsigned long long* __restrict__ table, int stride,
                                                                  const int* __restrict__ tableCount, const uint32_t* __restrict__ tileMask,
                                                                  const unsigned long long* __restrict__ superMask,
-                                                                 unsigned long long* scratch, uint8_t* __restrict__ flags,
+                                                                 unsigned long long* scratch, float4* recordsAll, uint8_t* __restrict__ flags,
                                                                  int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters) {
     __shared__ BinShared s_all[kBinWarps];
     const int warp = threadIdx.x >> 5;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-read (S2R) inside the loops
     BinShared& S = s_all[warp];
     unsigned long long* list = scratch + (size_t)(blockIdx.x * kBinWarps + warp) * stride;
+    float4* rec = recordsAll + (size_t)(blockIdx.x * kBinWarps + warp) * (kBinRecords + 32) * 4;
     unsigned long long myRays = 0, myEntries = 0;
     unsigned myTris = 0, myTiles = 0;  // statistics (lane 0 only matters)
 #ifdef IPP_VIS_DIAG
@@ -270,6 +272,56 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         myEntries += (unsigned long long)nEnt;
         __syncwarp();
 
+        // ---- phase 1.5: the pose half of the set-up, once per triangle of the list instead of once per tile that stages it ----
+        // (a leaf rectangle covers most of the 16 tiles, so a triangle is staged by ~10 of them).  The 64-byte records go to this
+        // warp's part of `recordsAll` (L2-resident) in list order and the entries are rewritten to name records instead of
+        // triangles; a list with more than kBinRecords triangles keeps the per-tile set-up.
+        bool cached;
+        {
+            int n = 0;
+            for (int i = lane; i < L; i += 32) n += (int)((unsigned)list[i] & kLeafMask);
+#pragma unroll
+            for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+            cached = n <= kBinRecords;
+        }
+        if (cached) {
+            TileGeom none = {};
+            const float zFarCull = zFar * kDepthTie;
+            int recBase = 0;
+            for (int base = 0; base < L; base += 32) {
+                const int i = base + lane;
+                const unsigned long long e = i < L ? list[i] : 0ull;
+                const int first = (int)(((unsigned)e & 0x0fffffffu) >> kLeafShift);
+                const int cnt = i < L ? (int)((unsigned)e & kLeafMask) : 0;
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+                for (int q = 0; q < cnt; ++q) S.queue[incl - cnt + q] = (uint8_t)((lane << 3) | q);
+                if (i < L) list[i] = (e & ~0x0fffffffull) | ((unsigned long long)(unsigned)(recBase + incl - cnt) << kLeafShift) | (unsigned)cnt;
+                __syncwarp();
+                for (int p0 = 0; p0 < total; p0 += 32) {
+                    const int p = p0 + lane;
+                    const unsigned b = p < total ? S.queue[p] : 0u;
+                    const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
+                    if (p < total) setup_triangle_t<true>(sc, &S.snap, tri, S.tri[lane], ox, oy, oz, zNear, zFarCull, none);
+                    __syncwarp();
+                    // 32 rows of 64 B in shared memory -> 2 KB of records, coalesced (rows past `total` are never read)
+                    const float4* src = reinterpret_cast<const float4*>(&S.tri[0][0]);
+                    float4* dst = rec + (size_t)(recBase + p0) * 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dst[k * 32 + lane] = src[k * 32 + lane];
+                    __syncwarp();
+                }
+                recBase += total;
+            }
+        }
+        __syncwarp();
+
         // ---- phase 2: the occupied tiles of the supertile ----
         for (int tl = 0; tl < 16; ++tl) {
             const int tx = (int)ssx * 4 + (tl & 3), ty = (int)ssy * 4 + (tl >> 2);
@@ -294,7 +346,10 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
             auto flush = [&](bool mineValid) {
                 __syncwarp();
                 bool mineOk = false;
-                if (mineValid) mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
+                if (mineValid) {
+                    if (cached) mineOk = stage_record(rec + (size_t)myTri * 4, S.tri[lane], zcull, tg);
+                    else mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
+                }
                 const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
 #ifdef IPP_VIS_DIAG
                 myLive += __popc(live);
@@ -418,6 +473,7 @@ int bins_grid_blocks() {
     return sms * perSM;
 }
 int bins_warps_per_block() { return kBinWarps; }
+size_t bins_record_floats_per_warp() { return (size_t)(kBinRecords + 32) * 16; }
 
 // size classes of the per-pose sort (threads x keys per thread); stride of a pose's table = capacity of its class
 struct SortClass { int capacity; };
@@ -452,7 +508,7 @@ void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, cons
     // counters[1] is the work cursor of this launch
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
     k_visibility_bins<<<grid, kBinThreads, 0, st>>>(sc, cam, d_snaps, d_superOffset, nSnaps, b.table, b.stride, b.tableCount, b.tileMask,
-                                                   b.superMask, b.scratch, d_flags, d_idImage, d_counters);
+                                                   b.superMask, b.scratch, b.records, d_flags, d_idImage, d_counters);
 #ifdef IPP_VIS_DIAG
     unsigned long long d[1];
     cudaStreamSynchronize(st);
