@@ -7,8 +7,10 @@
 //                 sorted by depth (cub::BlockRadixSort, stable, so the order is deterministic).  The CTA also ORs the rectangles
 //                 into a 32x32 tile occupancy mask and an 8x8 supertile mask: empty tiles are never scheduled.
 //   k_visibility_bins  persistent grid, one warp per occupied 128x128 supertile: one coalesced pass over the pose's table keeps the
-//                 entries that touch the supertile (per-warp list in an L2-resident scratch), then the warp rasterises its <= 16
-//                 tiles one after the other.  A tile walks the list front to back, queues the triangles of the leaves whose
+//                 entries that touch the supertile (per-warp list in an L2-resident scratch); the tile-independent half of the
+//                 triangle set-up then runs once per triangle of that list into 64-byte records (a second per-warp scratch), and
+//                 the warp rasterises its <= 16 tiles one after the other, staging records instead of setting triangles up
+//                 again in every tile.  A tile walks the list front to back, queues the triangles of the leaves whose
 //                 rectangle contains it, and stops at the first entry behind its farthest hit -- strict front-to-back order makes
 //                 the hierarchical depth culling of raster.cuh bite much earlier than the approximate order of a BVH walk, and
 //                 there is no dependent node fetch left on the critical path.
