@@ -375,9 +375,10 @@ def run_gpu(args):
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # K4 reads 8 B per leaf-bin entry it scans (BVH variant: 64 B per node a tile packet fetches) and 48 B per triangle it stages
-    # (DESIGN.md section 4); the counts are data dependent and come from the kernel's own device counters for exactly the timed
-    # launches ("nodes" is in 64-byte units for either variant).
+    # K4 reads 8 B per leaf-bin entry and 4 B per record header it scans (BVH variant: 64 B per node a tile packet fetches) and at
+    # least 48 B per triangle it sets up (48 B of vertices in, 64 B of record out) or stages (64 B record in) -- 48 B is charged
+    # for each; the counts are data dependent and come from the kernel's own device counters for exactly
+    # the timed launches ("nodes" is in 64-byte units for either variant).
     alg_bytes_launch = (64.0 * vstat["nodes"] + 48.0 * vstat["triangles"]) / max(1, vis_n)
     rays_launch = cnt["rays"] / max(1, vis_n)
     vis_launch_s = vis_ms / max(1, vis_n) * 1e-3
@@ -413,7 +414,7 @@ def run_gpu(args):
                      "peak_source": peak_src,
                      "survey_independent_ray_model": {"bytes_per_ray": b_ray, "gbs": rays_launch * b_ray / vis_launch_s / 1e9 if vis_launch_s > 0 else 0.0,
                                                       "note": "what one independent BVH descent per issued ray would have requested; a tile shares one leaf list"},
-                     "note": "bytes = 8 B per leaf-bin entry scanned (64 B per BVH node in the bvh variant) + 48 B per triangle staged, counted "
+                     "note": "bytes = 8 B per leaf-bin entry / 4 B per record header scanned (64 B per BVH node in the bvh variant) + 48 B per triangle set up or staged, counted "
                              "on the device; triangles and leaf tables are served from L1/L2 (ncu DRAM traffic in profiles/), the kernel is "
                              "instruction-issue bound, not HBM bound"},
         "roofline_plan_reduce": warm,

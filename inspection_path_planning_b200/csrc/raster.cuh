@@ -87,9 +87,19 @@ __device__ __forceinline__ void tile_init(float* __restrict__ St, int* __restric
 // 0.03 pixel).
 // kPoseOnly: the part that does not depend on the tile -- zcull is then the far bound of the pose, [14] receives the nearest vertex
 // depth itself and the tile test is left to stage_record() below, which repeats it with the same expressions.
+// It also reports, in *tilesOut, which of the 4 x 4 tiles of the 128 x 128 supertile `super` (bit = row * 4 + column) hold a pixel centre
+// inside the screen bounding box of the projected vertices widened by kBoxPadPx pixels (all 16 when a vertex is not in front of the
+// eye): a pixel centre that passes the three edge tests lies inside the projected triangle up to rounding << kBoxPadPx, so a tile
+// outside the mask gets no fragment of the triangle.  *tilesOut is left alone when the triangle is rejected.
+struct SuperGeom {
+    float X0, Y0;    // image-plane coordinates of the supertile's first pixel centre
+    float ipx, ipy;  // pixels per image-plane unit
+};
+constexpr float kBoxPadPx = 0.5f;
 template <bool kPoseOnly>
 __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
-                                                 float oy, float oz, float zNear, float zcull, const TileGeom& g) {
+                                                 float oy, float oz, float zNear, float zcull, const TileGeom& g,
+                                                 const SuperGeom* super = nullptr, unsigned* tilesOut = nullptr) {
     const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
     float valid = -1.f;
     if (b.w == 0.f) {  // not degenerate
@@ -123,6 +133,25 @@ __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Sn
             o[13] = a.w;  // triangle id (int bits)
             if constexpr (kPoseOnly) {
                 o[14] = zlo;
+                unsigned tiles = 0xffffu;
+                if (zlo > 1e-4f) {
+                    const float ra = rcp_approx(za), rb = rcp_approx(zb), rc = rcp_approx(zc);
+                    const float Xa = (float)ddot(ax, ay, az, sX, sY, sZ) * ra, Xb = (float)ddot(bx_, by_, bz_, sX, sY, sZ) * rb,
+                                Xc = (float)ddot(cx_, cy_, cz_, sX, sY, sZ) * rc;
+                    const float Ya = (float)ddot(ax, ay, az, uX, uY, uZ) * ra, Yb = (float)ddot(bx_, by_, bz_, uX, uY, uZ) * rb,
+                                Yc = (float)ddot(cx_, cy_, cz_, uX, uY, uZ) * rc;
+                    // in pixels from the supertile's first pixel centre: tile column c holds the centres 32 c .. 32 c + 31
+                    const float fx0 = fmaxf((fminf(Xa, fminf(Xb, Xc)) - super->X0) * super->ipx - kBoxPadPx, -512.f);
+                    const float fx1 = fminf((fmaxf(Xa, fmaxf(Xb, Xc)) - super->X0) * super->ipx + kBoxPadPx, 512.f);
+                    const float fy0 = fmaxf((fminf(Ya, fminf(Yb, Yc)) - super->Y0) * super->ipy - kBoxPadPx, -512.f);
+                    const float fy1 = fminf((fmaxf(Ya, fmaxf(Yb, Yc)) - super->Y0) * super->ipy + kBoxPadPx, 512.f);
+                    const int c0 = max(0, (int)ceilf((fx0 - 31.f) * 0.03125f)), c1 = min(3, (int)floorf(fx1 * 0.03125f));
+                    const int r0 = max(0, (int)ceilf((fy0 - 31.f) * 0.03125f)), r1 = min(3, (int)floorf(fy1 * 0.03125f));
+                    tiles = 0u;
+                    if (c0 <= c1 && r0 <= r1)
+                        tiles = (((2u << c1) - (1u << c0)) * 0x1111u) & ((16u << (4 * r1)) - 1u) & ~((1u << (4 * r0)) - 1u);
+                }
+                *tilesOut = tiles;
             } else {
             // can any pixel centre of the tile be inside?  Each edge function is monotone in X and in Y (also as computed), so its
             // value at the extreme pixel centre of the tile bounds it over the tile.

@@ -31,6 +31,10 @@ constexpr int kBinWarps = 4;
 constexpr int kBinThreads = kBinWarps * 32;
 constexpr unsigned long long kNoEntry = ~0ull;
 constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
+#ifndef IPP_STAGE_MIN
+#define IPP_STAGE_MIN 8
+#endif
+constexpr int kStageMin = IPP_STAGE_MIN;  // waiting records that make a staging round worth running at the end of a header chunk
 constexpr int kBinRecords = 4096;   // set-up triangles (64 B each) a warp can keep for one supertile
 #ifndef IPP_FILTER_UNROLL
 #define IPP_FILTER_UNROLL 4
@@ -212,7 +216,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-read (S2R) inside the loops
     BinShared& S = s_all[warp];
     unsigned long long* list = scratch + (size_t)(blockIdx.x * kBinWarps + warp) * stride;
-    float4* rec = recordsAll + (size_t)(blockIdx.x * kBinWarps + warp) * (kBinRecords + 32) * 4;
+    float4* rec = recordsAll + (size_t)(blockIdx.x * kBinWarps + warp) * ((kBinRecords + 32) * 17 / 4);
+    unsigned* hdr = reinterpret_cast<unsigned*>(rec + (size_t)(kBinRecords + 32) * 4);  // one word per record: leaf depth key:16 | tiles:16
+    uint16_t* q16 = reinterpret_cast<uint16_t*>(S.queue);                                // phase 2: records waiting for a staging round
     unsigned long long myRays = 0, myEntries = 0;
     unsigned myTris = 0, myTiles = 0;  // statistics (lane 0 only matters)
 #ifdef IPP_VIS_DIAG
@@ -279,15 +285,20 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         // warp's part of `recordsAll` (L2-resident) in list order and the entries are rewritten to name records instead of
         // triangles; a list with more than kBinRecords triangles keeps the per-tile set-up.
         bool cached;
+        int nRec = 0;
         {
-            int n = 0;
-            for (int i = lane; i < L; i += 32) n += (int)((unsigned)list[i] & kLeafMask);
+            for (int i = lane; i < L; i += 32) nRec += (int)((unsigned)list[i] & kLeafMask);
 #pragma unroll
-            for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
-            cached = n <= kBinRecords;
+            for (int d = 16; d; d >>= 1) nRec += __shfl_xor_sync(0xffffffffu, nRec, d);
+            cached = nRec <= kBinRecords;
         }
         if (cached) {
             TileGeom none = {};
+            SuperGeom sgm;
+            sgm.X0 = __fmaf_rn((float)((int)ssx * 4 * kTile), kx, cx);
+            sgm.Y0 = __fmaf_rn((float)((int)ssy * 4 * kTile), ky, cy);
+            sgm.ipx = 1.f / kx;
+            sgm.ipy = 1.f / ky;
             const float zFarCull = zFar * kDepthTie;
             int recBase = 0;
             for (int base = 0; base < L; base += 32) {
@@ -304,13 +315,18 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
                 for (int q = 0; q < cnt; ++q) S.queue[incl - cnt + q] = (uint8_t)((lane << 3) | q);
-                if (i < L) list[i] = (e & ~0x0fffffffull) | ((unsigned long long)(unsigned)(recBase + incl - cnt) << kLeafShift) | (unsigned)cnt;
                 __syncwarp();
+                myTris += total;
                 for (int p0 = 0; p0 < total; p0 += 32) {
                     const int p = p0 + lane;
                     const unsigned b = p < total ? S.queue[p] : 0u;
                     const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
-                    if (p < total) setup_triangle_t<true>(sc, &S.snap, tri, S.tri[lane], ox, oy, oz, zNear, zFarCull, none);
+                    const unsigned zq = __shfl_sync(0xffffffffu, (unsigned)(e >> 48), b >> 3);
+                    unsigned tiles = 0u;  // a rejected triangle is never staged
+                    if (p < total) {
+                        setup_triangle_t<true>(sc, &S.snap, tri, S.tri[lane], ox, oy, oz, zNear, zFarCull, none, &sgm, &tiles);
+                        hdr[recBase + p] = (zq << 16) | tiles;
+                    }
                     __syncwarp();
                     // 32 rows of 64 B in shared memory -> 2 KB of records, coalesced (rows past `total` are never read)
                     const float4* src = reinterpret_cast<const float4*>(&S.tri[0][0]);
@@ -370,6 +386,44 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                     }
                 }
             };
+            if (cached) {
+                // the record headers, front to back: a lane keeps the records whose triangle can touch this tile; 32 of them make a
+                // staging round
+                int nq = 0;
+                for (int base = 0; occupied && base < nRec; base += 32) {
+                    const float bound = zcull * 1.000001f + 1e-4f;
+                    const int i = base + lane;
+                    const unsigned h = i < nRec ? hdr[i] : 0xffff0000u;
+                    const float zl = (float)(h >> 16) * iq;
+                    // sorted by leaf depth: when the first record of the chunk is behind the farthest hit, so is everything after it
+                    if (__shfl_sync(0xffffffffu, zl, 0) > bound) break;
+                    myEntries += 16ull;  // 32 headers of 4 bytes
+                    const bool hit = i < nRec && ((h >> tl) & 1u) != 0u && zl <= bound;
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m == 0u) continue;
+                    myTris += __popc(m);
+                    if (hit) q16[nq + __popc(m & ltMask)] = (uint16_t)i;
+                    nq += __popc(m);
+                    __syncwarp();
+                    if (nq >= 32) {
+                        myTri = q16[lane];
+                        const uint16_t moved = q16[32 + lane];
+                        __syncwarp();
+                        q16[lane] = moved;
+                        nq -= 32;
+                        flush(true);
+                    } else if (nq >= kStageMin) {  // a short round now keeps the depth bound, and with it the early exit, fresh
+                        myTri = q16[lane];
+                        const bool mine = lane < nq;
+                        nq = 0;
+                        flush(mine);
+                    }
+                }
+                if (nq > 0) {
+                    myTri = q16[lane];
+                    flush(lane < nq);
+                }
+            } else {
             for (int base = 0; occupied && base < L; base += 32) {
                 float bound = zcull * 1.000001f + 1e-4f;
                 const int i = base + lane;
@@ -419,6 +473,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                 }
             }
             if (pend > 0) flush(lane < pend && myZ <= zcull * 1.000001f + 1e-4f);
+            }
             __syncwarp();
             // ---- the winners ----
             if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
@@ -475,7 +530,7 @@ int bins_grid_blocks() {
     return sms * perSM;
 }
 int bins_warps_per_block() { return kBinWarps; }
-size_t bins_record_floats_per_warp() { return (size_t)(kBinRecords + 32) * 16; }
+size_t bins_record_floats_per_warp() { return (size_t)(kBinRecords + 32) * 17; }  // 64-byte records + 4-byte headers
 
 // size classes of the per-pose sort (threads x keys per thread); stride of a pose's table = capacity of its class
 struct SortClass { int capacity; };
