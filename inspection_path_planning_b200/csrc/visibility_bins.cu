@@ -8,10 +8,12 @@
 //                 into a 32x32 tile occupancy mask and an 8x8 supertile mask: empty tiles are never scheduled.
 //   k_visibility_bins  persistent grid, one warp per occupied 128x128 supertile: one coalesced pass over the pose's table keeps the
 //                 entries that touch the supertile (per-warp list in an L2-resident scratch); the tile-independent half of the
-//                 triangle set-up then runs once per triangle of that list into 64-byte records (a second per-warp scratch), and
-//                 the warp rasterises its <= 16 tiles one after the other, staging records instead of setting triangles up
-//                 again in every tile.  A tile walks the list front to back, queues the triangles of the leaves whose
-//                 rectangle contains it, and stops at the first entry behind its farthest hit -- strict front-to-back order makes
+//                 triangle set-up then runs once per triangle of that list into 64-byte records (a second per-warp scratch) with
+//                 a 4-byte header each (depth key of the leaf, tiles of the supertile the triangle's screen box touches), and
+//                 the warp rasterises its <= 16 tiles one after the other: a tile scans the headers front to back, stages the
+//                 records that can touch it, and stops at the first header behind its farthest hit (a list with more triangles
+//                 than the record scratch holds keeps the older scheme: walk the leaves, set their triangles up per tile) --
+//                 strict front-to-back order makes
 //                 the hierarchical depth culling of raster.cuh bite much earlier than the approximate order of a BVH walk, and
 //                 there is no dependent node fetch left on the critical path.
 //
@@ -281,9 +283,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         __syncwarp();
 
         // ---- phase 1.5: the pose half of the set-up, once per triangle of the list instead of once per tile that stages it ----
-        // (a leaf rectangle covers most of the 16 tiles, so a triangle is staged by ~10 of them).  The 64-byte records go to this
-        // warp's part of `recordsAll` (L2-resident) in list order and the entries are rewritten to name records instead of
-        // triangles; a list with more than kBinRecords triangles keeps the per-tile set-up.
+        // (a leaf rectangle covers most of the 16 tiles, so a triangle was set up by ~10 of them).  The 64-byte records and their
+        // 4-byte headers go to this warp's part of `recordsAll` (L2-resident) in list order; a list with more than kBinRecords
+        // triangles keeps the leaf walk with its per-tile set-up.
         bool cached;
         int nRec = 0;
         {
