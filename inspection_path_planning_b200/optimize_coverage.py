@@ -51,6 +51,29 @@ class Parameters:
                 raise AttributeError("unknown parameter " + k)
             setattr(self, k, v)
 
+    @classmethod
+    def names(cls):
+        return [k for k in vars(cls) if k.isupper()]
+
+    def as_dict(self):
+        return {k: copy.deepcopy(getattr(self, k)) for k in self.names()}
+
+    def write_python(self, path):
+        """A settings/Parameters.py for this run: one `NAME = value` line per parameter (multiRun keeps it beside the runs)."""
+        with open(path, "w") as f:
+            f.write("# experiment parameters (inspection_path_planning_b200.optimize_coverage.Parameters)\n")
+            for k, v in self.as_dict().items():
+                f.write("%s = %r\n" % (k, v))
+        return path
+
+    @classmethod
+    def from_python(cls, path):
+        """Reads a parameter file as multirun does (optimize_coverage.py:223-227); names this class does not know are ignored."""
+        scope = {}
+        with open(path) as f:
+            exec(compile(f.read(), path, "exec"), {"__builtins__": {}}, scope)
+        return cls(**{k: v for k, v in scope.items() if k.isupper() and hasattr(cls, k)})
+
 
 FITNESS_WEIGHTS = (-1, -1)  # settings/Constants_and_Datastructures.py:59-60: both objectives minimised
 
@@ -333,7 +356,7 @@ def initial_population(evaluator, params, seeds, num_boxes, max_energy, rng, sta
     return pop
 
 
-def run_nsga2(evaluator, params, seed=None, use_seeds=True, log=None, on_generation=None):
+def run_nsga2(evaluator, params, seed=None, use_seeds=True, log=None, on_generation=None, on_seeds=None):
     """main_nsga2 (:112-213).  Returns (population, pareto_front, logbook, stats)."""
     rng = random.Random(seed)
     stats = {"evaluations": 0, "calls": 0, "eval_s": 0.0, "memoised_edges": 0}
@@ -346,6 +369,9 @@ def run_nsga2(evaluator, params, seed=None, use_seeds=True, log=None, on_generat
             seeds.append(Individual([[int(g[0])] + ([] if params.SIMPLIFIED_VIEW_ANGLE else [0.0]) for g in plan]))  # initializeFromList
         evaluate_batch(evaluator, seeds, params, stats)  # storeSeedFitnesses :35-43
     stats["seed_s"] = time.perf_counter() - t0
+    stats["seed_individuals"] = seeds
+    if on_seeds and seeds:
+        on_seeds(seeds, stats["seed_s"])
 
     pop = initial_population(evaluator, params, seeds, num_boxes, max_energy, rng, stats)
     evaluate_batch(evaluator, [i for i in pop if i.fitness is None], params, stats)
@@ -439,34 +465,78 @@ def make_evaluator(scene, params, post_processing=False):
     return cpp_binding.PlanCoverageEstimator(scene, params.SENSOR_PARAMETERS, post_processing, params.PLAN_ORIGIN, params.PLAN_LOOPS_AROUND, True)
 
 
-def main(argv=None):
+PARAMETERS_SUBFOLDER = "experiment_parameters"  # settings/Constants_and_Datastructures.py:46-50
+SEED_PLAN_FILES = ("base_plans.pkl", "base_plans.yml")
+FINAL_POPULATION_FILES = ("winner_indivs.pkl", "winner_indivs.yml")
+
+
+def store_run_info(storage_folder, params):
+    """Utilities.store_run_info (:84-90): the parameters of an experiment next to its runs."""
+    folder = os.path.join(storage_folder, PARAMETERS_SUBFOLDER)
+    os.makedirs(folder, exist_ok=True)
+    return params.write_python(os.path.join(folder, "Parameters.py"))
+
+
+def main(argv=None, evaluator_factory=None):
+    """optimize_coverage.py:216-270.  evaluator_factory(scene, params, post_processing) replaces make_evaluator (tests)."""
     ap = argparse.ArgumentParser(description="NSGA-II inspection path planning on the batched B200 plan evaluator")
     ap.add_argument("-i", "--input_model_path", required=True)
     ap.add_argument("-o", "--output_folder", required=True)
     ap.add_argument("--disable_seeding", action="store_true")
-    ap.add_argument("--generations", type=int, default=Parameters.NUM_GENERATIONS)
-    ap.add_argument("--pop", type=int, default=Parameters.NUM_INDIVS)
+    ap.add_argument("--multirun", action="store_true",
+                    help="one run of an experiment: parameters come from <output_folder>/../experiment_parameters/Parameters.py, "
+                         "only the population stores are written")
+    ap.add_argument("--no_post_processing", action="store_true", help="only optimise and store the populations; no plan_ymls/")
+    ap.add_argument("--params", help="a Parameters.py to take the parameters from")
+    ap.add_argument("--generations", type=int)
+    ap.add_argument("--pop", type=int)
     ap.add_argument("--seed", type=int, default=None)
-    ap.add_argument("--image_height", type=int, default=1024)
+    ap.add_argument("--image_height", type=int)
     args = ap.parse_args(argv)
-    sp = list(Parameters.SENSOR_PARAMETERS)
-    sp[3] = args.image_height
-    params = Parameters(NUM_INDIVS=args.pop, NUM_GENERATIONS=args.generations, SENSOR_PARAMETERS=sp)
+    make = evaluator_factory or make_evaluator
+    if args.multirun:
+        # one level above the run's folder (:223-227); the run folder itself may not exist yet
+        params = Parameters.from_python(os.path.join(os.path.dirname(os.path.abspath(os.path.normpath(args.output_folder))),
+                                                     PARAMETERS_SUBFOLDER, "Parameters.py"))
+    elif args.params:
+        params = Parameters.from_python(args.params)
+    else:
+        params = Parameters()
+    if args.pop is not None:
+        params.NUM_INDIVS = args.pop
+    if args.generations is not None:
+        params.NUM_GENERATIONS = args.generations
+    if args.image_height is not None:
+        sp = list(params.SENSOR_PARAMETERS)
+        sp[3] = args.image_height
+        params.SENSOR_PARAMETERS = sp
+    os.makedirs(args.output_folder, exist_ok=True)
     t0 = time.time()
-    ev = make_evaluator(args.input_model_path, params)
+    ev = make(args.input_model_path, params, False)
+
+    def on_seeds(seeds, elapsed):  # storeSeedFitnesses :35-43
+        for name in SEED_PLAN_FILES:
+            store_population_and_parameters(seeds, name, args.output_folder, args.input_model_path, params, ev, elapsed_time=elapsed)
 
     def on_gen(gen, pop, pf):
         if params.STORAGE_INTERVAL != -1 and gen % params.STORAGE_INTERVAL == 0:
-            store_population_and_parameters(pop, "gen%d.yml" % gen, args.output_folder, args.input_model_path, params, ev)
+            for ext in ("pkl", "yml"):
+                store_population_and_parameters(pop, "gen%d.%s" % (gen, ext), args.output_folder, args.input_model_path, params, ev)
 
-    pop, pf, logbook, stats = run_nsga2(ev, params, seed=args.seed, use_seeds=not args.disable_seeding, log=print, on_generation=on_gen)
-    store_population_and_parameters(pop, "winner_indivs.yml", args.output_folder, args.input_model_path, params, ev, pf, time.time() - t0,
-                                    stats["memoised_edges"])
-    store_population_and_parameters(pop, "winner_indivs.pkl", args.output_folder, args.input_model_path, params, ev, pf, time.time() - t0,
-                                    stats["memoised_edges"])
+    pop, pf, logbook, stats = run_nsga2(ev, params, seed=args.seed, use_seeds=not args.disable_seeding, log=print, on_generation=on_gen,
+                                        on_seeds=on_seeds)
+    for name in FINAL_POPULATION_FILES:
+        store_population_and_parameters(pop, name, args.output_folder, args.input_model_path, params, ev, pf, time.time() - t0,
+                                        stats["memoised_edges"])
     hv = hypervolume_2d([i.fitness for i in pf], params.HYPERVOLUME_REF_POINT)
     print("pareto front %d plans, hypervolume %.4f; %d evaluations in %d batched calls, %.3f s in the evaluator, %.3f s total" % (
         len(pf), hv, stats["evaluations"], stats["calls"], stats["eval_s"], stats["total_s"]))
+    if not args.multirun and not args.no_post_processing:
+        # the reference also stores pictures of the plans here (GL viewer, out of scope); the waypoint files are exported
+        from . import plan_exporter
+        if hasattr(ev, "close"):
+            ev.close()
+        plan_exporter.export_all_winner_individuals(args.output_folder, evaluator=make(args.input_model_path, params, True))
     return 0
 
 

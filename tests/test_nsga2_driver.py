@@ -1,5 +1,6 @@
 """The caller side of the hot path: NSGA-II pieces restated from DEAP, the generational loop of
 plan_optimizer/optimize_coverage.py with one batched evaluator call per generation, and the result-store dictionaries."""
+import os
 import random
 
 import numpy as np
@@ -201,3 +202,47 @@ def test_generational_loop_with_view_angle_genes(oracle_mod):
     assert any(g[1] != 0.0 for ind in pop for g in ind)  # offsets were mutated and kept
     for ind in pop[:4]:
         assert tuple(ev.evaluatePlan(list(ind), True, 3, False)) == pytest.approx(ind.fitness)
+
+
+def test_parameter_file_round_trip(tmp_path):
+    p = oc.Parameters(NUM_INDIVS=12, PLAN_ORIGIN=[1.0, 2.0, 3.0], SIMPLIFIED_VIEW_ANGLE=False)
+    path = p.write_python(str(tmp_path / "Parameters.py"))
+    q = oc.Parameters.from_python(path)
+    assert q.as_dict() == p.as_dict() and q.NUM_INDIVS == 12 and q.PLAN_ORIGIN == [1.0, 2.0, 3.0]
+    (tmp_path / "other.py").write_text("NUM_GENERATIONS = 3\nNOT_A_PARAMETER = 1\nlowercase = 2\n")
+    r = oc.Parameters.from_python(str(tmp_path / "other.py"))
+    assert r.NUM_GENERATIONS == 3 and not hasattr(r, "NOT_A_PARAMETER") and r.NUM_INDIVS == oc.Parameters.NUM_INDIVS
+
+
+def test_command_line_run_and_multirun_store_what_the_reference_stores(oracle_mod, tmp_path):
+    """optimize_coverage.py:216-270 and multiRun.py:14-27 with the CPU evaluator standing in: base_plans, genN, winner_indivs as
+    .pkl and .yml, plan_ymls/ for a normal run; parameters read from experiment_parameters/ and no plan_ymls/ in a multirun."""
+    from inspection_path_planning_b200 import multi_run
+
+    def factory(scene, params, post_processing):
+        return oracle_mod.Oracle(scene, params.SENSOR_PARAMETERS, post_processing, params.PLAN_ORIGIN, params.PLAN_LOOPS_AROUND)
+
+    out = tmp_path / "single"
+    assert oc.main(["-i", mesh_path("sphere"), "-o", str(out), "--generations", "2", "--pop", "8", "--image_height", "32", "--seed", "5"],
+                   factory) == 0
+    stored = sorted(os.listdir(out / "populations"))
+    assert stored == ["base_plans.pkl", "base_plans.yml", "gen0.pkl", "gen0.yml", "winner_indivs.pkl", "winner_indivs.yml"]
+    win = oc.load_dumped_population(str(out / "populations" / "winner_indivs.yml"))
+    assert len(win["population"]) == 8 and win["sensor_params"][3] == 32 and win["elapsed_time"] > 0
+    base = oc.load_dumped_population(str(out / "populations" / "base_plans.pkl"))
+    assert len(base["population"]) > 0 and all(p["fitness"] is not None for p in base["population"]) and base["pareto_front"] is None
+    assert sorted(os.listdir(out / "plan_ymls")) == sorted("plan_%d.yml" % i for i in range(8))
+
+    exp = tmp_path / "experiment"
+    assert multi_run.main(["-i", mesh_path("sphere"), "-o", str(exp), "--runs", "2", "--generations", "1", "--pop", "8",
+                           "--image_height", "32", "--seed", "3"], factory) == 0
+    stored_params = oc.Parameters.from_python(str(exp / "experiment_parameters" / "Parameters.py"))
+    assert stored_params.NUM_INDIVS == 8 and stored_params.NUM_GENERATIONS == 1 and stored_params.SENSOR_PARAMETERS[3] == 32
+    for i in range(2):
+        run = exp / ("run%d" % i)
+        assert "winner_indivs.pkl" in os.listdir(run / "populations") and not (run / "plan_ymls").exists()
+        d = oc.load_dumped_population(str(run / "populations" / "winner_indivs.pkl"))
+        assert len(d["population"]) == 8 and d["sensor_params"][3] == 32
+    a = oc.load_dumped_population(str(exp / "run0" / "populations" / "winner_indivs.pkl"))["population"]
+    b = oc.load_dumped_population(str(exp / "run1" / "populations" / "winner_indivs.pkl"))["population"]
+    assert [p["genotype1"] for p in a] != [p["genotype1"] for p in b]  # run i uses seed + i
