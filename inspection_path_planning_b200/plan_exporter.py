@@ -13,8 +13,11 @@ Like the reference's exporter (evolutionary_operators/planEvaluatorSetup.py:13-2
 evaluator with postProcessing=True: every exported heading comes from the heading search towards the primitives
 (OsgHelpers.cpp:451-489: render both perpendicular directions along the edge, keep the one that shows more surface).
 
-The reference's sharp-turn splitting
-(split_sharply_turning_waypoints, :37-81) calls a split_waypoint() that is defined nowhere in its tree; it is not restated.
+Sharp-turn splitting (split_sharply_turning_waypoints, :34-81, `--min_turn_angle`): the reference calls a split_waypoint() that
+is defined nowhere in its tree; split_waypoint() here does what the comment above its call site says -- "two new waypoints
+instead of the old one, one split_distance metres before it, the other split_distance after", the edge between them heading
+"as the average of the orientation before and after" -- with one guard the comment does not have: a new waypoint never moves
+further than half of its edge away from the corner.
 """
 import argparse
 import math
@@ -31,13 +34,55 @@ def rotate_about_z(vectors, degrees):
     return [R @ np.asarray(v, dtype=np.float64) for v in vectors]
 
 
-def plan_to_waypoints(evaluator, plan, position_offsets=None, rotation_degrees_around_z=0.0):
+def angle_between(v1, v2):
+    """settings/Utilities.py:213-230: angle in radians between two vectors (0 for a zero vector)."""
+    n1, n2 = np.linalg.norm(v1), np.linalg.norm(v2)
+    if n1 == 0.0 or n2 == 0.0:
+        return 0.0
+    return float(np.arccos(np.clip(np.dot(v1 / n1, v2 / n2), -1.0, 1.0)))
+
+
+def split_waypoint(incoming, outgoing, corner, heading_before, heading_after, split_distance):
+    """The corner waypoint becomes two: one split_distance before it on the incoming edge, one split_distance after it on the
+    outgoing edge (at most half of either edge); the edge between them looks along the average of the two headings."""
+    li, lo = np.linalg.norm(incoming), np.linalg.norm(outgoing)
+    before = corner - incoming / li * min(split_distance, 0.5 * li)
+    after = corner + outgoing / lo * min(split_distance, 0.5 * lo)
+    between = np.asarray(heading_before, dtype=np.float64) + np.asarray(heading_after, dtype=np.float64)
+    n = np.linalg.norm(between)
+    between = between / n if n > 0.0 else np.asarray(heading_before, dtype=np.float64)  # opposite headings: keep the first
+    return before, after, between
+
+
+def split_sharply_turning_waypoints(positions, headings, min_turn_angle=0.785398, split_distance=4.0):
+    """plan_exporter.py:34-81.  headings[k] is the heading on the way to positions[k + 1]; the first and the last waypoint are
+    never split.  Returns (positions, headings) with one more of each per split corner."""
+    positions = [np.asarray(p, dtype=np.float64) for p in positions]
+    new_pos, new_head = [positions[0]], []
+    for k in range(len(headings) - 1):
+        start, corner, nxt = positions[k], positions[k + 1], positions[k + 2]
+        incoming, outgoing = corner - start, nxt - corner
+        if angle_between(incoming, outgoing) > abs(min_turn_angle):
+            before, after, between = split_waypoint(incoming, outgoing, corner, headings[k], headings[k + 1], split_distance)
+            new_pos += [before, after]
+            new_head += [np.asarray(headings[k], dtype=np.float64), between]
+        else:
+            new_pos.append(corner)
+            new_head.append(np.asarray(headings[k], dtype=np.float64))
+    new_pos.append(positions[-1])
+    new_head.append(np.asarray(headings[-1], dtype=np.float64))
+    return new_pos, new_head
+
+
+def plan_to_waypoints(evaluator, plan, position_offsets=None, rotation_degrees_around_z=0.0, min_turn_angle=None):
     """-> list of {"position": {x, y, z}, "orientation": {r, p, y}} for one plan (list of [id] genes)."""
     if len(plan) == 0:
         return []
     positions, headings = evaluator.interpretAndExportPlan(plan, [], [])
     positions = [np.asarray(p, dtype=np.float64) for p in positions]
     headings = [np.asarray(h, dtype=np.float64) for h in headings]
+    if min_turn_angle and len(headings) > 1:
+        positions, headings = split_sharply_turning_waypoints(positions, headings, min_turn_angle)
     if rotation_degrees_around_z:
         positions = rotate_about_z(positions, rotation_degrees_around_z)
         headings = rotate_about_z(headings, rotation_degrees_around_z)
@@ -52,9 +97,9 @@ def plan_to_waypoints(evaluator, plan, position_offsets=None, rotation_degrees_a
     return out
 
 
-def export_plan_to_yaml(evaluator, plan, yaml_path, position_offsets=None, rotation_degrees_around_z=0.0):
+def export_plan_to_yaml(evaluator, plan, yaml_path, position_offsets=None, rotation_degrees_around_z=0.0, min_turn_angle=None):
     import yaml
-    wps = plan_to_waypoints(evaluator, plan, position_offsets, rotation_degrees_around_z)
+    wps = plan_to_waypoints(evaluator, plan, position_offsets, rotation_degrees_around_z, min_turn_angle)
     if not wps:
         return None
     with open(yaml_path, "w") as f:
@@ -62,7 +107,8 @@ def export_plan_to_yaml(evaluator, plan, yaml_path, position_offsets=None, rotat
     return yaml_path
 
 
-def export_all_winner_individuals(results_root, position_offsets=None, rotation_degrees_around_z=0.0, evaluator=None):
+def export_all_winner_individuals(results_root, position_offsets=None, rotation_degrees_around_z=0.0, evaluator=None,
+                                  min_turn_angle=None):
     """plan_exporter.py:180-200: every plan of populations/winner_indivs.(pkl|yml) -> plan_ymls/plan_<i>.yml"""
     from . import optimize_coverage as oc
     pop_dir = os.path.join(results_root, "populations")
@@ -78,7 +124,7 @@ def export_all_winner_individuals(results_root, position_offsets=None, rotation_
     paths = []
     for i, ind in enumerate(data["population"]):
         paths.append(export_plan_to_yaml(evaluator, ind["genotype1"], os.path.join(out_dir, "plan_%d.yml" % i), position_offsets,
-                                         rotation_degrees_around_z))
+                                         rotation_degrees_around_z, min_turn_angle))
     return paths
 
 
@@ -87,8 +133,10 @@ def main(argv=None):
     ap.add_argument("-i", "--input_folder", required=True)
     ap.add_argument("--position_offset", type=float, nargs=3)
     ap.add_argument("--rotation_offset", type=float, help="radians about +z")
+    ap.add_argument("--min_turn_angle", type=float, help="radians; a turn sharper than this is split into two")
     a = ap.parse_args(argv)
-    export_all_winner_individuals(a.input_folder, a.position_offset, math.degrees(a.rotation_offset) if a.rotation_offset else 0.0)
+    export_all_winner_individuals(a.input_folder, a.position_offset, math.degrees(a.rotation_offset) if a.rotation_offset else 0.0,
+                                  min_turn_angle=a.min_turn_angle)
     return 0
 
 

@@ -246,3 +246,32 @@ def test_command_line_run_and_multirun_store_what_the_reference_stores(oracle_mo
     a = oc.load_dumped_population(str(exp / "run0" / "populations" / "winner_indivs.pkl"))["population"]
     b = oc.load_dumped_population(str(exp / "run1" / "populations" / "winner_indivs.pkl"))["population"]
     assert [p["genotype1"] for p in a] != [p["genotype1"] for p in b]  # run i uses seed + i
+
+
+def test_sharp_turns_are_split_into_two_waypoints():
+    """plan_exporter.split_sharply_turning_waypoints (:34-81): a U-turn corner becomes two waypoints split_distance before and
+    after it, the edge between them heading along the average of the two headings; gentle corners and the end points stay."""
+    import math
+    from inspection_path_planning_b200 import plan_exporter as pe
+
+    class Fake:
+        def interpretAndExportPlan(self, plan, a, b):
+            pos = [(0.0, 0.0, 5.0), (20.0, 0.0, 5.0), (20.0, 20.0, 5.0), (21.0, 40.0, 5.0), (21.0, 43.0, 5.0), (24.0, 43.0, 5.0)]
+            head = [(0.0, 1.0, 0.0), (-1.0, 0.0, 0.0), (-1.0, 0.0, 0.0), (-1.0, 0.0, 0.0), (0.0, -1.0, 0.0)]
+            return pos, head
+
+    assert pe.angle_between(np.array([1.0, 0, 0]), np.array([0, 1.0, 0])) == pytest.approx(math.pi / 2)
+    assert pe.angle_between(np.zeros(3), np.array([0, 1.0, 0])) == 0.0
+    plain = pe.plan_to_waypoints(Fake(), [[0]] * 6)
+    split = pe.plan_to_waypoints(Fake(), [[0]] * 6, min_turn_angle=math.pi / 4)
+    assert len(plain) == 6 and len(split) == 8  # the right angles at (20, 0) and (21, 43) are split, the 3 degree bend is not
+    xy = [(w["position"]["x"], w["position"]["y"]) for w in split]
+    assert xy[0] == (0.0, 0.0) and xy[-1] == (24.0, 43.0)
+    assert xy[1] == pytest.approx((16.0, 0.0)) and xy[2] == pytest.approx((20.0, 4.0))  # 4 m before and after the corner
+    assert xy[3] == pytest.approx((20.0, 20.0))
+    assert xy[5] == pytest.approx((21.0, 41.5)) and xy[6] == pytest.approx((22.5, 43.0))  # short edges: half the edge at most
+    yaw = [w["orientation"]["y"] for w in split]
+    assert yaw[1] == pytest.approx(math.pi / 2)                       # on the way to the first new waypoint: the old heading
+    assert yaw[2] == pytest.approx(math.atan2(1.0, -1.0))             # between the two: the average of (0, 1) and (-1, 0)
+    assert yaw[3] == pytest.approx(math.pi) and yaw[7] == pytest.approx(-math.pi / 2)
+    assert all(w["position"]["z"] == 5.0 for w in split)
