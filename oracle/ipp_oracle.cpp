@@ -412,6 +412,8 @@ struct Oracle {
     // scratch item buffer
     std::vector<double> zbuf;
     std::vector<int32_t> idbuf;
+    std::vector<double> z1;  // edge-epsilon classification: per pixel and sample position
+    std::vector<int32_t> idWide, idNarrow;
     size_t W32() const { return (T + 31) / 32; }
 
     // ---- setup ----
@@ -847,6 +849,39 @@ struct Oracle {
         return true;
     }
 
+    // Columns [xa, xb] of image row Y (inside [x0, x1]) outside which no pixel centre can pass the coverage test of frag() or
+    // frag_dilated(): a pure accelerator of the loops below (long thin triangles have bounding boxes hundreds of times their
+    // area), the per-pixel tests are unchanged.  Conservative: every edge function may miss its sign by `slack` image-plane units
+    // times its gradient plus a rounding allowance, and the interval is widened by a pixel on either side.
+    static inline bool row_span(const Setup& S, const Cam& cam, double Y, double slack, int x0, int x1, int& xa, int& xb) {
+        const double* N[3] = {S.na, S.nb, S.nc};
+        double loP = -INFINITY, hiP = INFINITY, loN = -INFINITY, hiN = INFINITY;
+        bool okP = true, okN = true;
+        for (int k = 0; k < 3; ++k) {
+            const double n0 = N[k][0], n1y = N[k][1] * Y, c = n1y + N[k][2];
+            const double g = std::sqrt(n0 * n0 + N[k][1] * N[k][1]);
+            const double m = slack * g + 1e-9 * (std::fabs(n0) * cam.tanX + std::fabs(n1y) + std::fabs(N[k][2]));
+            if (n0 > 0) {
+                loP = std::max(loP, (-m - c) / n0);
+                hiN = std::min(hiN, (m - c) / n0);
+            } else if (n0 < 0) {
+                hiP = std::min(hiP, (-m - c) / n0);
+                loN = std::max(loN, (m - c) / n0);
+            } else {
+                if (c < -m) okP = false;
+                if (c > m) okN = false;
+            }
+        }
+        if (!(loP <= hiP)) okP = false;
+        if (!(loN <= hiN)) okN = false;
+        if (!okP && !okN) return false;
+        const double lo = std::min(okP ? loP : INFINITY, okN ? loN : INFINITY), hi = std::max(okP ? hiP : -INFINITY, okN ? hiN : -INFINITY);
+        const double fa = (lo / cam.tanX + 1.0) * 0.5 * cam.W - 0.5, fb = (hi / cam.tanX + 1.0) * 0.5 * cam.W - 0.5;
+        xa = !(fa > x0) ? x0 : (fa >= x1 + 2 ? x1 + 1 : std::max(x0, (int)std::floor(fa) - 1));
+        xb = !(fb < x1) ? x1 : (fb <= x0 - 2 ? x0 - 1 : std::min(x1, (int)std::ceil(fb) + 1));
+        return xa <= xb;
+    }
+
     void render(const V3& eye, const V3& center, const V3& up, Bits& seen, Bits* strictSeen, Bits* lenientSeen) {
         nSnapshots++;
         nPixels += (uint64_t)imgW * imgH;
@@ -863,7 +898,9 @@ struct Oracle {
                 if (!S.ok) continue;
                 for (int py = S.y0; py <= S.y1; ++py) {
                     double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
-                    for (int px = S.x0; px <= S.x1; ++px) {
+                    int xa, xb;
+                    if (!row_span(S, cam, Y, 0.0, S.x0, S.x1, xa, xb)) continue;
+                    for (int px = xa; px <= xb; ++px) {
                         double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
                         double t;
                         if (!frag(S, X, Y, t)) continue;
@@ -890,15 +927,20 @@ struct Oracle {
         const double lenLo = zNear * (1 - d), lenHi = zFar * (1 + d), strLo = zNear * (1 + d), strHi = zFar * (1 - d);
         const double bandWide = (1.0 + DEPTH_TIE_REL) * (1 + d), bandNarrow = (1.0 + DEPTH_TIE_REL) * (1 - d);
         // z1: nearest depth per sample position; idWide / idNarrow: lowest ID inside the widened / narrowed tie band
-        std::vector<double> z1(NP * K, INFINITY);
-        std::vector<int32_t> idWide(NP * K, -1), idNarrow(NP * K, -1);
+        z1.assign(NP * K, INFINITY);
+        idWide.assign(NP * K, -1);
+        idNarrow.assign(NP * K, -1);
+        // every sample position and the dilated test lie within this distance (image-plane units) of the pixel centre's own test
+        const double spanSlack = std::max(ex, ey) * 1.5 + ex + ey;
         for (int pass = 0; pass < 2; ++pass) {
             for (size_t i = 0; i < T; ++i) {
                 setup_tri(cam, i, S);
                 if (!S.ok) continue;
                 for (int py = S.y0; py <= S.y1; ++py) {
                     double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
-                    for (int px = S.x0; px <= S.x1; ++px) {
+                    int xa, xb;
+                    if (!row_span(S, cam, Y, spanSlack, S.x0, S.x1, xa, xb)) continue;
+                    for (int px = xa; px <= xb; ++px) {
                         double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
                         size_t pix = ((size_t)py * W + px) * K;
                         if (pass == 1) {
