@@ -106,6 +106,11 @@ int ipp_update_memoised_edges(ipp_t* h, const int32_t* ids, const float* angles,
                               int64_t* remaining);
 /* number of edge bitmaps currently memoised */
 int64_t ipp_memo_size(const ipp_t* h);
+/* The reference's memo is a std::map that never refuses an entry (PlanCoverageEstimator.cpp:70,102-110); the edge-bitmap row pool
+ * here is finite (70 % of the free device memory, or IPP_CACHE_GB).  When the new edges of a call do not fit, the rows of edges the
+ * call does not use are dropped, and a population that still needs more rows than the pool holds is evaluated in pieces; results
+ * never depend on what was cached.  This returns how often rows were dropped that way since the evaluator was made. */
+int64_t ipp_evictions(const ipp_t* h);
 /* drop all memoised edges and collision flags */
 int ipp_clear_memo(ipp_t* h);
 
@@ -158,8 +163,9 @@ int ipp_counters(ipp_t* h, int64_t* out8, int reset);
  * binned variant), [1] triangles staged (48 B each), [2] 32x32-pixel tiles rasterised, [3] pixel-centre rays, and, only when the
  * library was built with -DIPP_VIS_DIAG (they cost 2 % of the kernel; 0 otherwise), for the binned variant [4] staged triangles that
  * survived set-up (can produce a fragment in their tile), [5] tiles in which some ray never hit, so that the leaf list was walked
- * to its end */
-int ipp_visibility_stats(ipp_t* h, int64_t* out6, int reset);
+ * to its end; binned variant, always: [6] 128x128 supertiles rasterised from cached set-up records (the path the 1024-pixel
+ * configurations take), [7] supertiles whose triangle list overflowed the record scratch and took the leaf walk */
+int ipp_visibility_stats(ipp_t* h, int64_t* out8, int reset);
 /* which edge-visibility kernel renders the item buffers: 1 = depth-sorted leaf bins per 128x128 supertile (the default when the
  * mesh has <= 16384 BVH leaves and the image is <= 1024 pixels a side), 0 = BVH frustum walk per tile.  Same sampling rule and
  * rasteriser either way.  *out_active (nullable) receives the variant in force after the call; use_bins < 0 only queries. */

@@ -38,6 +38,7 @@ PROTOTYPES = {
     "ipp_evaluate_population_device": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "ipp_update_memoised_edges": (C.c_int, [H, c_i32p, c_f32p, c_i64p, C.c_int64, c_i64p]),
     "ipp_memo_size": (C.c_int64, [H]),
+    "ipp_evictions": (C.c_int64, [H]),
     "ipp_clear_memo": (C.c_int, [H]),
     "ipp_interpret_plan": (C.c_int, [H, c_f64p, C.c_int, C.c_int, c_f64p, c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ipp_edge_bitmap": (C.c_int, [H, C.c_int, C.c_int, C.c_double, c_u32p]),

@@ -236,16 +236,59 @@ class PlanCoverageEstimator(object):
         """Multi-GPU form (after comm_init): every rank passes the same whole population.  The edges nobody has rendered yet are
         rendered once across the ranks and their bitmap rows exchanged (NCCL all-gather), then this rank evaluates its contiguous
         shard and one more all-gather returns every plan's fitness row to every rank."""
-        ids, offsets = plans if isinstance(plans, tuple) else pack_population(plans)
+        if isinstance(plans, tuple):
+            ids, angles, offsets = (plans[0], None, plans[1]) if len(plans) == 2 else plans
+        else:
+            ids, angles, offsets = pack_population(plans, with_angles=True)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         pop = offsets.size - 1
         fit = out if out is not None else np.empty((pop, 4), dtype=np.float64)
-        _lib.check(self._L.ipp_evaluate_population_sharded(self._h, ids.ctypes.data_as(_lib.c_i32p), None, offsets.ctypes.data_as(_lib.c_i64p),
+        _lib.check(self._L.ipp_evaluate_population_sharded(self._h, ids.ctypes.data_as(_lib.c_i32p), _fp(angles), offsets.ctypes.data_as(_lib.c_i64p),
                                                            pop, int(bool(memoization)), int(bool(disableEnergyLimit)), _dp(fit)))
+        return fit
+
+    def evaluatePopulationResident(self, plans, memoization=True, disableEnergyLimit=False):
+        """The device-resident entry point (ipp_evaluate_population_device) behind a convenience wrapper: the population is put
+        into device memory first, the call itself only sees device pointers, the fitness rows are read back afterwards."""
+        if isinstance(plans, tuple):
+            ids, angles, offsets = (plans[0], None, plans[1]) if len(plans) == 2 else plans
+        else:
+            ids, angles, offsets = pack_population(plans, with_angles=True)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        pop, n_genes = offsets.size - 1, int(ids.size)
+        fit = np.zeros((pop, 4), dtype=np.float64)
+        if pop == 0:
+            return fit
+        bufs = []
+
+        def dev(arr):
+            p = C.c_void_p()
+            _lib.check(self._L.ipp_device_alloc(self._h, max(int(arr.nbytes), 16), C.byref(p)))
+            bufs.append(p)
+            if arr.nbytes:
+                _lib.check(self._L.ipp_memcpy_h2d(self._h, p, arr.ctypes.data_as(C.c_void_p), int(arr.nbytes)))
+            return p
+        try:
+            d_ids, d_off, d_fit = dev(ids), dev(offsets), dev(fit)
+            d_ang = dev(angles) if angles is not None else None
+            _lib.check(self._L.ipp_evaluate_population_device(self._h, d_ids, d_ang, d_off, pop, n_genes, int(bool(memoization)),
+                                                              int(bool(disableEnergyLimit)), d_fit))
+            self.sync()
+            _lib.check(self._L.ipp_memcpy_d2h(self._h, fit.ctypes.data_as(C.c_void_p), d_fit, int(fit.nbytes)))
+        finally:
+            for p in bufs:
+                self._L.ipp_device_free(self._h, p)
         return fit
 
     # ---- scene facts and test hooks ----
     def memo_size(self):
         return int(self._L.ipp_memo_size(self._h))
+
+    def evictions(self):
+        """How often the finite edge-bitmap row pool ran full and dropped the rows of edges the running call did not use."""
+        return int(self._L.ipp_evictions(self._h))
 
     def clear_memo(self):
         _lib.check(self._L.ipp_clear_memo(self._h))
@@ -355,9 +398,10 @@ class PlanCoverageEstimator(object):
         return dict(zip(keys, (int(x) for x in out)))
 
     def visibility_stats(self, reset=False):
-        out = np.zeros(6, dtype=np.int64)
+        out = np.zeros(8, dtype=np.int64)
         _lib.check(self._L.ipp_visibility_stats(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
-        return dict(zip(["nodes", "triangles", "tiles", "rays", "live_triangles", "open_tiles"], (int(x) for x in out)))
+        return dict(zip(["nodes", "triangles", "tiles", "rays", "live_triangles", "open_tiles", "supertiles_records", "supertiles_leaf_walk"],
+                        (int(x) for x in out)))
 
     def visibility_variant(self, use_bins=None):
         """Selects (True / False) or queries (None) the edge-visibility kernel: leaf bins or BVH walk per tile."""

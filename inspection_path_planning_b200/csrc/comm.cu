@@ -59,6 +59,8 @@ struct Comm {
     int32_t* d_ids = nullptr;
     int64_t* d_offsets = nullptr;
     int64_t idsCap = 0, offCap = 0;
+    float* d_angles = nullptr;
+    int64_t anglesCap = 0;
     int32_t* d_allIds = nullptr;  // whole population (shared edge rendering)
     int64_t* d_allOffsets = nullptr;
     int64_t allIdsCap = 0, allOffCap = 0;
@@ -91,6 +93,7 @@ void comm_destroy(Comm* c) {
     cudaFree(c->d_gather);
     cudaFree(c->d_ids);
     cudaFree(c->d_offsets);
+    cudaFree(c->d_angles);
     cudaFree(c->d_allIds);
     cudaFree(c->d_allOffsets);
     delete c;
@@ -126,10 +129,24 @@ void comm_eval_device_and_allgather(Evaluator& ev, const int32_t* d_ids, const f
     cudaStream_t st = ev.stream();
     if (mine > per) throw std::invalid_argument("libipp: shard larger than the per-rank slot");
     double* d_mine = d_gather + (size_t)c->rank * per * 4;
-    // rows of the last (short) shard that hold no plan are zero
-    if (mine < per) IPP_CUDA_CHECK(cudaMemsetAsync(d_mine + mine * 4, 0, (size_t)(per - mine) * 4 * sizeof(double), st));
-    // plan_reduce writes this rank's rows straight into its slot of the gather buffer: no staging copy before the collective
-    if (mine > 0) ev.evaluatePopulationDevice(d_ids, d_angles, d_offsets, mine, nGenes, memo, noLimit, d_mine, nullptr);
+    // A failure on one rank only (a bad box id in its shard, an allocation) must not leave the others waiting in the collective:
+    // the ranks agree on an error flag first and throw together.
+    std::string localError;
+    try {
+        // rows of the last (short) shard that hold no plan are zero
+        if (mine < per) IPP_CUDA_CHECK(cudaMemsetAsync(d_mine + mine * 4, 0, (size_t)(per - mine) * 4 * sizeof(double), st));
+        // plan_reduce writes this rank's rows straight into its slot of the gather buffer: no staging copy before the collective
+        if (mine > 0) ev.evaluatePopulationDevice(d_ids, d_angles, d_offsets, mine, nGenes, memo, noLimit, d_mine, nullptr);
+    } catch (const std::exception& e) {
+        localError = e.what();
+        if (localError.empty()) localError = "unknown error";
+    }
+    double failed = localError.empty() ? 0.0 : 1.0;
+    comm_allreduce(c, &failed, 1, 1, st);
+    if (failed != 0.0) {
+        if (localError.find("out of range") != std::string::npos) throw std::out_of_range(localError);
+        throw std::runtime_error(localError.empty() ? "libipp: another rank failed while it evaluated its shard of the population" : localError);
+    }
     // the one exchange step: every rank receives every shard's fitness rows over NVLink
     nccl_check(api().AllGather(d_mine, d_gather, (size_t)per * 4, ncclDouble, c->comm, st), "ncclAllGather");
 }
@@ -138,7 +155,6 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
                              int64_t lo, int64_t hi, bool memo, bool noLimit, double* fitness) {
     Comm* c = ev.comm_;
     cudaStream_t st = ev.stream();
-    if (angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
     const int64_t mine = hi - lo;
     const int64_t g0 = offsets[lo], nGenes = offsets[hi] - g0;
     if (c->world * per * 4 > c->gatherCap) {
@@ -158,15 +174,23 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
     }
     std::vector<int64_t> off((size_t)mine + 1);
     for (int64_t i = 0; i <= mine; ++i) off[i] = offsets[lo + i] - g0;
+    if (angles && nGenes + 1 > c->anglesCap) {
+        cudaFree(c->d_angles);
+        c->anglesCap = nGenes + nGenes / 4 + 16;
+        IPP_CUDA_CHECK(cudaMalloc(&c->d_angles, (size_t)c->anglesCap * sizeof(float)));
+    }
     if (mine > 0) {
         IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_ids, ids + g0, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_offsets, off.data(), (size_t)(mine + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (angles) IPP_CUDA_CHECK(cudaMemcpyAsync(c->d_angles, angles + g0, (size_t)nGenes * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     // The edges of the WHOLE population are rendered once across the ranks and exchanged (second exchange step of this path: the
     // fresh bitmap rows), so that a rank does not render an edge its shard shares with another rank's shard.  Skipped when no
     // shard uses an edge its rank has not got: the steady state of a memoised run costs one probe kernel and one all-reduce.
     // (memoization == false keeps the reference's meaning -- nothing rendered for this call is remembered -- and renders per shard)
-    if (c->world > 1 && pop > 0 && c->shareEdges && memo) {
+    // ([id, offset] genes and post-processing evaluators render per shard: the first keeps its memo on the host, keyed by the
+    // offset bits; the second chooses every heading by rendering both candidates.)
+    if (c->world > 1 && pop > 0 && c->shareEdges && memo && !angles && !ev.postProcessing_) {
         double unseen = (double)ev.countUnseenEdges(c->d_ids, c->d_offsets, mine, noLimit);
         comm_allreduce(c, &unseen, 1, 1, st);
         if (unseen > 0) {
@@ -187,7 +211,7 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
             ev.renderEdgesShared(c->d_allIds, c->d_allOffsets, pop, noLimit, cx);
         }
     }
-    comm_eval_device_and_allgather(ev, c->d_ids, nullptr, c->d_offsets, mine, nGenes, per, memo, noLimit, c->d_gather);
+    comm_eval_device_and_allgather(ev, c->d_ids, angles ? c->d_angles : nullptr, c->d_offsets, mine, nGenes, per, memo, noLimit, c->d_gather);
     IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, c->d_gather, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     IPP_CUDA_CHECK(cudaStreamSynchronize(st));
 }

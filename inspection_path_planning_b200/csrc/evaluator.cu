@@ -95,9 +95,10 @@ Evaluator::Evaluator(const std::string& scenePath, const double specs[8], bool p
 
     // ---- scalars ----
     d_scalars_ = dalloc<int>(8);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, 8 * sizeof(int), stream_));
     IPP_CUDA_CHECK(cudaHostAlloc((void**)&h_scalars_, 8 * sizeof(int), cudaHostAllocDefault));
-    d_visCounters_ = dalloc<unsigned long long>(8);
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
+    d_visCounters_ = dalloc<unsigned long long>(16);
+    IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 16 * sizeof(unsigned long long), stream_));
     d_angleOne_ = dalloc<float>(1);
 
     // ---- candidate viewpoints (PlanInterpreterBoxOrder::divideIntoBoxes :193-251) ----
@@ -209,7 +210,7 @@ Evaluator::~Evaluator() {
     cudaStreamSynchronize(stream_);
     free_bvh(scene_);
     cudaFree(scene_.area);
-    cudaFree(d_pos_); cudaFree(d_coll_); cudaFree(d_rowmap_); cudaFree(d_used_); cudaFree(d_newKeys_);
+    cudaFree(d_pos_); cudaFree(d_coll_); cudaFree(d_rowmap_); cudaFree(d_used_); cudaFree(d_evictUsed_); cudaFree(d_newKeys_);
     cudaFree(d_scalars_); cudaFreeHost(h_scalars_); cudaFree(d_rows_); cudaFree(d_freeStack_);
     cudaFree(d_flags_); cudaFree(d_rowOfSlot_); cudaFree(d_counts_); cudaFree(d_snapOffset_);
     cudaFree(d_snaps_); cudaFree(d_ntiles_); cudaFree(d_tileOffset_); cudaFree(d_scanTmp_);
@@ -297,18 +298,19 @@ void Evaluator::counters(int64_t out[8], bool reset) {
     out[4] = nCollisionQueries_; out[5] = nReduceLaunches_; out[6] = nPlansReduced_; out[7] = nRowsRead_;
     if (reset) {
         nLaunches_ = nSnapshots_ = nEdgesRendered_ = nCollisionQueries_ = nReduceLaunches_ = nPlansReduced_ = nRowsRead_ = 0;
-        IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 16 * sizeof(unsigned long long), stream_));
     }
 }
-void Evaluator::visibilityStats(int64_t out[6], bool reset) {
+void Evaluator::visibilityStats(int64_t out[8], bool reset) {
     bind();
-    unsigned long long c[8];
+    unsigned long long c[16];
     IPP_CUDA_CHECK(cudaMemcpyAsync(c, d_visCounters_, sizeof(c), cudaMemcpyDeviceToHost, stream_));
     sync();
     // out[0]: 64-byte units of acceleration-structure data fetched = BVH nodes (visibility.cu) + 8-byte bin entries / 8 (visibility_bins.cu)
     out[0] = (int64_t)c[2] + (int64_t)(c[5] / 8); out[1] = (int64_t)c[3]; out[2] = (int64_t)c[4]; out[3] = (int64_t)c[0];
     out[4] = (int64_t)c[6]; out[5] = (int64_t)c[7];  // binned variant only
-    if (reset) IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 8 * sizeof(unsigned long long), stream_));
+    out[6] = (int64_t)c[8]; out[7] = (int64_t)c[9];  // supertiles rasterised from set-up records / by the leaf walk (overflow)
+    if (reset) IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 16 * sizeof(unsigned long long), stream_));
 }
 void Evaluator::timerStart() {
     bind();
@@ -480,7 +482,7 @@ void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles, b
     for (int b0 = 0, n = 0; b0 < nNew; b0 += n) {
         int64_t snaps = 0;
         for (n = 0; b0 + n < nNew && n < batchCap_ && (n == 0 || snaps + perEdge[b0 + n] <= maxSnapsPerBatch_); ++n) snaps += perEdge[b0 + n];
-        launch_assign_rows(d_keys + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
+        launch_assign_rows(d_keys + b0, n, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, (int)rowCapacity_, d_scalars_ + 4, stream_);
         renderBatch(d_keys + b0, d_angles ? d_angles + b0 : nullptr, n, d_rowOfSlot_);
         if (publish) launch_publish_rows(d_keys + b0, d_rowOfSlot_, n, d_rowmap_, stream_);
         if (rowsOut) {
@@ -490,6 +492,11 @@ void Evaluator::renderKeys(const int* d_keys, int nNew, const float* d_angles, b
         nLaunches_ += 2;
     }
     if (publish) liveRows_ += nNew;
+    readScalars();
+    if (h_scalars_[4]) {
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 4, 0, sizeof(int), stream_));
+        throw std::logic_error("libipp: internal error: the edge-bitmap row pool ran dry while rows were being assigned");
+    }
 }
 
 int64_t Evaluator::countUnseenEdges(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit) {
@@ -526,42 +533,74 @@ int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offs
     }
     // 1. collision flags of the whole population (replicated: a millisecond per 20 k edges), energy gate, then the edges
     //    whose bitmap nobody has yet
-    PlanMarkArgs mk;
-    mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
-    mk.active = nullptr; mk.coll = d_coll_; mk.rowmap = nullptr; mk.used = nullptr; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
-    mk.errFlag = d_scalars_ + 3;
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 3, 0, sizeof(int), stream_));
-    launch_mark_collisions(mk, stream_);
-    nLaunches_++;
-    readScalars();
-    if (h_scalars_[3]) throw std::out_of_range("libipp: box id out of range");
-    if (h_scalars_[0] > 0) {
-        launch_collide_keys(scene_, d_newKeys_, h_scalars_[0], d_pos_, N_, d_coll_, stream_);
+    // 2. every rank must have found the same set (same population, same memo contents); every decision below is taken on
+    //    all-reduced values, so the ranks take the same branch and no rank leaves the others waiting in a collective:
+    //      * the ranks disagree (their memos diverged, e.g. one of them had to evict rows while it evaluated its shard): every
+    //        rank clears its memo and marks again; a second disagreement means different populations and is an error;
+    //      * the new rows do not fit: the rows of edges the population does not use are evicted everywhere, and if that is
+    //        not enough the shared rendering is skipped (-1): every rank then renders what its own shard needs, in pieces
+    //        (coverageRange), and the next shared call starts from cleared memos.
+    int nNew = 0;
+    bool evicted = false;
+    for (int round = 0;; ++round) {
+        PlanMarkArgs mk;
+        mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
+        mk.active = nullptr; mk.coll = d_coll_; mk.rowmap = nullptr; mk.used = nullptr; mk.newKeys = d_newKeys_; mk.newCount = d_scalars_;
+        mk.errFlag = d_scalars_ + 3;
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 3, 0, sizeof(int), stream_));
+        launch_mark_collisions(mk, stream_);
         nLaunches_++;
-        nCollisionQueries_ += h_scalars_[0];
+        readScalars();
+        const bool badId = h_scalars_[3] != 0;
+        if (h_scalars_[0] > 0) {
+            launch_collide_keys(scene_, d_newKeys_, h_scalars_[0], d_pos_, N_, d_coll_, stream_);
+            nLaunches_++;
+            nCollisionQueries_ += h_scalars_[0];
+        }
+        if (badId) throw std::out_of_range("libipp: box id out of range");  // (the same population on every rank: all of them throw)
+        PlanEnergyArgs en;
+        en.ids = d_ids; en.offsets = d_offsets; en.pop = pop; en.N = N_; en.hasStart = hasStart_; en.loops = loops_;
+        en.pos = d_pos_; en.coll = d_coll_; en.collisionPenalty = collisionPenalty_; en.maxEnergy = maxAllowedEnergy_;
+        en.disableLimit = noLimit; en.fitness = d_fitShared_; en.active = d_activeShared_;
+        launch_energy(en, stream_);
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+        mk.active = d_activeShared_; mk.coll = nullptr; mk.rowmap = d_rowmap_;
+        launch_mark_rows(mk, stream_);
+        nLaunches_ += 2;
+        readScalars();
+        nNew = h_scalars_[0];
+        const int freeRows = h_scalars_[1];
+        double agree[3] = {(double)nNew, -(double)nNew, nNew > freeRows ? 1.0 : 0.0};
+        cx.allReduceMax(agree, 3, stream_);
+        if (agree[0] != (double)nNew || agree[1] != -(double)nNew || memoDiverged_) {
+            launch_unclaim_rows(d_newKeys_, nNew, d_rowmap_, stream_);
+            nLaunches_++;
+            if (round > 0 && !memoDiverged_)
+                throw std::runtime_error("libipp: the ranks disagree on the new edges of the population (different populations)");
+            memoDiverged_ = false;
+            clearMemo();
+            continue;
+        }
+        if (nNew == 0) return 0;
+        if (agree[2] == 0.0) break;
+        launch_unclaim_rows(d_newKeys_, nNew, d_rowmap_, stream_);
+        nLaunches_++;
+        if (evicted) {
+            memoDiverged_ = true;  // (every rank takes this branch)
+            return -1;
+        }
+        PlanMarkArgs keep = mk;
+        keep.rowmap = nullptr; keep.used = d_evictUsed();
+        launch_fill_u8(keep.used, nKeys_, 0, stream_);
+        launch_mark_rows(keep, stream_);
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 2, 0, sizeof(int), stream_));
+        launch_gc_rows(d_rowmap_, keep.used, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
+        nLaunches_ += 3;
+        liveRows_ = readInt(d_scalars_ + 2);
+        nEvictions_++;
+        evicted = true;
     }
-    PlanEnergyArgs en;
-    en.ids = d_ids; en.offsets = d_offsets; en.pop = pop; en.N = N_; en.hasStart = hasStart_; en.loops = loops_;
-    en.pos = d_pos_; en.coll = d_coll_; en.collisionPenalty = collisionPenalty_; en.maxEnergy = maxAllowedEnergy_;
-    en.disableLimit = noLimit; en.fitness = d_fitShared_; en.active = d_activeShared_;
-    launch_energy(en, stream_);
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
-    mk.active = d_activeShared_; mk.coll = nullptr; mk.rowmap = d_rowmap_;
-    launch_mark_rows(mk, stream_);
-    nLaunches_ += 2;
-    readScalars();
-    const int nNew = h_scalars_[0], freeRows = h_scalars_[1];
-    // 2. every rank must have found the same set (same population, same memo contents)
-    //    (the cache-full condition is agreed on too: no rank may leave the others waiting in a collective)
-    double agree[3] = {(double)nNew, -(double)nNew, nNew > freeRows ? 1.0 : 0.0};
-    cx.allReduceMax(agree, 3, stream_);
-    if (agree[0] != (double)nNew || agree[1] != -(double)nNew)
-        throw std::runtime_error("libipp: the ranks disagree on the new edges of the population (different populations or memo contents)");
-    if (nNew == 0) return 0;
-    if (agree[2] != 0.0)
-        throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
-                                 " free rows); call updateMemoisedEdges or evaluate a smaller batch");
     // 3. the same order everywhere, and a random one: neighbouring keys (edges leaving the same viewpoint) cost alike, contiguous
     //    chunks of the ascending order gave one rank of two 1.65x the mean work
     if (!d_sortedKeys_) d_sortedKeys_ = dalloc<int>(nKeys_);
@@ -599,7 +638,7 @@ int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offs
             const int qN = std::max(0, std::min(B, qhi - (qlo + s0)));
             if (qN == 0) continue;
             const int* keys = d_sortedKeys_ + qlo + s0;
-            launch_assign_rows(keys, qN, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, stream_);
+            launch_assign_rows(keys, qN, d_rowmap_, d_rowOfSlot_, d_freeStack_, d_scalars_ + 1, (int)rowCapacity_, d_scalars_ + 4, stream_);
             launch_rows_scatter(d_exchange_ + (size_t)q * B * rowWords_, d_rowOfSlot_, qN, d_rows_, rowWords_, stream_);
             launch_publish_rows(keys, d_rowOfSlot_, qN, d_rowmap_, stream_);
             nLaunches_ += 3;
@@ -608,6 +647,12 @@ int64_t Evaluator::renderEdgesShared(const int32_t* d_ids, const int64_t* d_offs
     }
     sync();
     return hi - lo;
+}
+
+int Evaluator::headingChunk() const { return std::max(1, std::min(nKeys_ / 2, batchCap_)); }
+uint8_t* Evaluator::d_evictUsed() {
+    if (!d_evictUsed_) d_evictUsed_ = dalloc<uint8_t>(nKeys_);
+    return d_evictUsed_;
 }
 
 double* Evaluator::reducePartials(int64_t pop) {
@@ -642,15 +687,17 @@ void Evaluator::energyAndGate(const int32_t* d_ids, const int64_t* d_offsets, in
     groupEnd(KG_PLAN);
     nLaunches_++;
     readScalars();
-    if (h_scalars_[3]) throw std::out_of_range("libipp: box id out of range");
+    const bool badId = h_scalars_[3] != 0;
     int nColl = h_scalars_[0];
     if (nColl > 0) {
+        // (also when a plan carried a bad id: the flags the other plans claimed are resolved, none is left pending)
         groupBegin(KG_COLLISION);
         launch_collide_keys(scene_, d_newKeys_, nColl, d_pos_, N_, d_coll_, stream_);
         groupEnd(KG_COLLISION);
         nLaunches_++;
         nCollisionQueries_ += nColl;
     }
+    if (badId) throw std::out_of_range("libipp: box id out of range");
 
     // 2. energy + gate
     PlanEnergyArgs en;
@@ -667,42 +714,97 @@ void Evaluator::energyAndGate(const int32_t* d_ids, const int64_t* d_offsets, in
 void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t pop,
                                          int64_t nGenes, bool memo, bool noLimit, double* d_fitness, uint32_t* unionBitmapHost) {
     bind();
-    if (d_angles) throw std::invalid_argument("libipp: [id, angle] genes are not supported by the batched path yet");
     if (pop <= 0) return;
-    energyAndGate(d_ids, d_offsets, pop, noLimit, d_fitness);
-    PlanMarkArgs mk;
-    mk.ids = d_ids; mk.offsets = d_offsets; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
-    mk.newKeys = d_newKeys_; mk.newCount = d_scalars_; mk.errFlag = d_scalars_ + 3; mk.used = nullptr;
-
-    groupBegin(KG_PLAN);
-    // 3. edge bitmaps never seen before -> K3, K4, pack
-    IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
-    mk.active = d_active_; mk.coll = nullptr; mk.rowmap = d_rowmap_;
-    const bool wantUsed = unionBitmapHost != nullptr;
-    if (wantUsed) {
-        launch_fill_u8(d_used_, nKeys_, 0, stream_);
-        mk.used = d_used_;
-        nLaunches_++;
+    if (d_angles) {
+        // [id, angleOffset] genes: the memo of their edges is keyed on the host (edge key, offset bits), so the genes come back once
+        // (12 bytes per gene); everything else stays where it is
+        std::vector<int32_t> ids((size_t)nGenes);
+        std::vector<float> angles((size_t)nGenes);
+        std::vector<int64_t> offsets((size_t)pop + 1);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(ids.data(), d_ids, (size_t)nGenes * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(angles.data(), d_angles, (size_t)nGenes * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(offsets.data(), d_offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, stream_));
+        sync();
+        if (offsets[0] != 0 || offsets[pop] != nGenes) throw std::invalid_argument("libipp: offsets must start at 0 and end at n_genes");
+        evaluatePopulationAngles(ids.data(), angles.data(), offsets.data(), pop, memo, noLimit, d_ids, d_offsets, d_fitness, unionBitmapHost);
+        return;
     }
-    launch_mark_rows(mk, stream_);
-    groupEnd(KG_PLAN);
-    nLaunches_++;
-    readScalars();
-    int nNew = h_scalars_[0];
+    energyAndGate(d_ids, d_offsets, pop, noLimit, d_fitness);
+    const bool wantUnion = unionBitmapHost != nullptr;
+    if (wantUnion) IPP_CUDA_CHECK(cudaMemsetAsync(d_union_, 0, (size_t)rowWords_ * 4, stream_));
+    coverageRange(d_ids, d_offsets, 0, pop, memo, d_fitness, wantUnion);
+    if (wantUnion) {
+        IPP_CUDA_CHECK(cudaMemcpyAsync(unionBitmapHost, d_union_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
+        sync();
+    }
+}
+
+// Steps 3-4 of evaluatePlan for the plans [lo, hi) of a population whose energy gate has run (d_active_): edge bitmaps the memo
+// does not hold -> K3, K4, pack; then K6.  The reference's memo is a std::map that never refuses an entry
+// (PlanCoverageEstimator.cpp:70,102-110); the row pool here is finite, so when the new edges of the range do not fit, the rows of
+// edges the range does not use are evicted first (they would be re-rendered on their next use, exactly as after
+// updateMemoisedEdges), and if the range still needs more rows than the pool has it is evaluated in two halves, recursively.
+// Results do not depend on what was cached.
+void Evaluator::coverageRange(const int32_t* d_ids, const int64_t* d_offsets, int64_t lo, int64_t hi, bool memo, double* d_fitness,
+                              bool wantUnion) {
+    const int64_t pop = hi - lo;
+    if (pop <= 0) return;
+    PlanMarkArgs mk;
+    mk.ids = d_ids; mk.offsets = d_offsets + lo; mk.pop = pop; mk.N = N_; mk.hasStart = hasStart_; mk.loops = loops_;
+    mk.newKeys = d_newKeys_; mk.newCount = d_scalars_; mk.errFlag = d_scalars_ + 3; mk.used = nullptr;
+    mk.active = d_active_ + lo; mk.coll = nullptr; mk.rowmap = d_rowmap_;
+
+    int nNew = 0;
+    for (int attempt = 0;; ++attempt) {
+        groupBegin(KG_PLAN);
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_, 0, sizeof(int), stream_));
+        if (wantUnion) {
+            launch_fill_u8(d_used_, nKeys_, 0, stream_);
+            mk.used = d_used_;
+            nLaunches_++;
+        }
+        launch_mark_rows(mk, stream_);
+        groupEnd(KG_PLAN);
+        nLaunches_++;
+        readScalars();
+        nNew = h_scalars_[0];
+        const int64_t freeRows = h_scalars_[1];
+        // the heading search renders both candidate headings of a chunk of edges before it hands the losers' rows back
+        const int64_t need = postProcessing_ ? (int64_t)nNew + std::min<int64_t>(nNew, headingChunk()) : nNew;
+        if (need <= freeRows) break;
+        launch_unclaim_rows(d_newKeys_, nNew, d_rowmap_, stream_);
+        nLaunches_++;
+        if (attempt == 0) {
+            // evict what this range does not use
+            PlanMarkArgs keep = mk;
+            keep.rowmap = nullptr; keep.used = d_evictUsed();
+            launch_fill_u8(keep.used, nKeys_, 0, stream_);
+            launch_mark_rows(keep, stream_);
+            IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 2, 0, sizeof(int), stream_));
+            launch_gc_rows(d_rowmap_, keep.used, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
+            nLaunches_ += 3;
+            liveRows_ = readInt(d_scalars_ + 2);
+            nEvictions_++;
+            continue;
+        }
+        if (pop == 1)
+            throw std::runtime_error("libipp: the edge-bitmap cache (" + std::to_string(rowCapacity_) + " rows) cannot hold the " +
+                                     std::to_string(need) + " edges of a single plan");
+        const int64_t mid = lo + pop / 2;
+        coverageRange(d_ids, d_offsets, lo, mid, memo, d_fitness, wantUnion);
+        coverageRange(d_ids, d_offsets, mid, hi, memo, d_fitness, wantUnion);
+        return;
+    }
     if (nNew > 0) {
-        int freeRows = h_scalars_[1];
-        if (nNew > freeRows)
-            throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
-                                     " free rows); call updateMemoisedEdges or evaluate a smaller batch");
         if (postProcessing_) renderKeysHeadingSearch(d_newKeys_, nNew);
         else renderNewEdges(nNew, nullptr);
     }
 
     // 4. OR + area-weighted popcount
     PlanReduceArgs rd;
-    rd.ids = d_ids; rd.offsets = d_offsets; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
-    rd.active = d_active_; rd.rowmap = d_rowmap_; rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
-    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness; rd.partial = reducePartials(pop);
+    rd.ids = d_ids; rd.offsets = d_offsets + lo; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
+    rd.active = d_active_ + lo; rd.rowmap = d_rowmap_; rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
+    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness + 4 * lo; rd.partial = reducePartials(pop);
     groupBegin(KG_REDUCE);
     launch_plan_reduce(rd, numSMs_, stream_);
     groupEnd(KG_REDUCE);
@@ -710,26 +812,16 @@ void Evaluator::evaluatePopulationDevice(const int32_t* d_ids, const float* d_an
     nReduceLaunches_++;
     nPlansReduced_ += pop;
 
-    if (wantUsed) {
+    if (wantUnion) {
         launch_union_rows(d_used_, nKeys_, d_rowmap_, d_rows_, rowWords_, d_union_, stream_);
         nLaunches_++;
-        IPP_CUDA_CHECK(cudaMemcpyAsync(unionBitmapHost, d_union_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
-        sync();
     }
     if (!memo && nNew > 0) {
         // memoization == false: edges rendered for this call are not remembered (evaluatePlanInternal,
-        // PlanCoverageEstimator.cpp:128-151); hand their rows back
-        // (reuse the collector with used = 1 everywhere except the new keys)
-        std::vector<int> keys(nNew);
-        IPP_CUDA_CHECK(cudaMemcpyAsync(keys.data(), d_newKeys_, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-        sync();
-        std::vector<uint8_t> used(nKeys_, 1);
-        for (int k : keys) used[k] = 0;
-        IPP_CUDA_CHECK(cudaMemcpyAsync(d_used_, used.data(), nKeys_, cudaMemcpyHostToDevice, stream_));
-        IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 2, 0, sizeof(int), stream_));
-        launch_gc_rows(d_rowmap_, d_used_, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
-        nLaunches_ += 2;
-        liveRows_ = readInt(d_scalars_ + 2);
+        // PlanCoverageEstimator.cpp:128-151); their rows go straight back
+        launch_unpublish_rows(d_newKeys_, nNew, d_rowmap_, d_freeStack_, d_scalars_ + 1, stream_);
+        nLaunches_++;
+        liveRows_ -= nNew;
     }
 }
 
@@ -749,54 +841,122 @@ inline uint64_t angle_key(int key, float angle) {
 }  // namespace
 
 void Evaluator::evaluatePopulationAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo, bool noLimit,
-                                         double* fitness, uint32_t* unionBitmap) {
+                                         const int32_t* d_ids, const int64_t* d_offsets, double* d_fitness, uint32_t* unionBitmap) {
+    requireQuickHeading();
     const int64_t nGenes = offsets[pop];
     for (int64_t g = 0; g < nGenes; ++g)
         if (ids[g] < 0 || ids[g] >= N_) throw std::out_of_range("libipp: box id out of range");
-    energyAndGate(d_ids_, d_offsets_, pop, noLimit, d_fitness_);
+    energyAndGate(d_ids, d_offsets, pop, noLimit, d_fitness);
     std::vector<uint8_t> active(pop);
     IPP_CUDA_CHECK(cudaMemcpyAsync(active.data(), d_active_, (size_t)pop, cudaMemcpyDeviceToHost, stream_));
-    readScalars();  // also synchronises; [1] = free rows
-    const int freeRows = h_scalars_[1];
+    sync();
+    if (unionBitmap) IPP_CUDA_CHECK(cudaMemsetAsync(d_union_, 0, (size_t)rowWords_ * 4, stream_));
+    anglesRange(ids, angles, offsets, active.data(), 0, pop, memo, d_ids, d_offsets, d_fitness, unionBitmap != nullptr);
+    if (unionBitmap) IPP_CUDA_CHECK(cudaMemcpyAsync(unionBitmap, d_union_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
+    sync();
+}
 
-    // the edges of the plans that passed the gate: memoised row, or a slot of this call's new (key, offset) pairs
-    std::vector<int64_t> edgeOffsets(pop + 1, 0);
+void Evaluator::rowListToDevice(const std::vector<int>& list) {
+    if ((int64_t)list.size() > rowListCap_) {
+        cudaFree(d_rowList_);
+        rowListCap_ = (int64_t)list.size() + (int64_t)list.size() / 4 + 16;
+        d_rowList_ = dalloc<int>(rowListCap_);
+    }
+    if (!list.empty()) IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowList_, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+}
+
+// coverage of the plans [lo, hi) of a population of [id, offset] genes (the gate has run: active[]).  A row pool too small for the
+// new (edge, offset) pairs of the range first drops every memo entry the range does not use, then halves the range (see coverageRange).
+void Evaluator::anglesRange(const int32_t* ids, const float* angles, const int64_t* offsets, const uint8_t* active, int64_t lo, int64_t hi,
+                            bool memo, const int32_t* d_ids, const int64_t* d_offsets, double* d_fitness, bool wantUnion) {
+    const int64_t pop = hi - lo;
+    if (pop <= 0) return;
+    std::vector<int64_t> edgeOffsets;
     std::vector<int> edgeRows;  // >= 0 row, < 0: -(slot + 1)
     std::vector<int> newKeys;
     std::vector<float> newAngles;
     std::unordered_map<uint64_t, int> slotOf;
-    for (int64_t p = 0; p < pop; ++p) {
-        const int64_t lo = offsets[p], n = offsets[p + 1] - lo;
-        if (active[p] && n > 0) {
-            // node sequence [start] g_0 .. g_{n-1} [g_0 if the plan loops around]; the offset of an edge is its end node's
-            int prev = hasStart_ ? N_ : ids[lo];
-            const int64_t firstEnd = hasStart_ ? 0 : 1, ends = n + (loops_ ? 1 : 0);
-            for (int64_t k = firstEnd; k < ends; ++k) {
-                const int64_t gk = k < n ? k : 0;
-                const int cur = ids[lo + gk];
-                const float ang = angles[lo + gk];
-                const int key = prev * N_ + cur;
-                const uint64_t mk = angle_key(key, ang);
-                auto it = angleMemo_.find(mk);
-                if (it != angleMemo_.end()) {
-                    edgeRows.push_back(it->second);
-                } else {
-                    auto ins = slotOf.emplace(mk, (int)newKeys.size());
-                    if (ins.second) {
-                        newKeys.push_back(key);
-                        newAngles.push_back(ang);
+    for (int attempt = 0;; ++attempt) {
+        edgeOffsets.assign(pop + 1, 0);
+        edgeRows.clear(); newKeys.clear(); newAngles.clear(); slotOf.clear();
+        // the edges of the plans that passed the gate: memoised row, or a slot of this call's new (key, offset) pairs
+        for (int64_t p = lo; p < hi; ++p) {
+            const int64_t g0 = offsets[p], n = offsets[p + 1] - g0;
+            if (active[p] && n > 0) {
+                // node sequence [start] g_0 .. g_{n-1} [g_0 if the plan loops around]; the offset of an edge is its end node's
+                int prev = hasStart_ ? N_ : ids[g0];
+                const int64_t firstEnd = hasStart_ ? 0 : 1, ends = n + (loops_ ? 1 : 0);
+                for (int64_t k = firstEnd; k < ends; ++k) {
+                    const int64_t gk = k < n ? k : 0;
+                    const int cur = ids[g0 + gk];
+                    const float ang = angles[g0 + gk];
+                    const int key = prev * N_ + cur;
+                    const uint64_t mk = angle_key(key, ang);
+                    auto it = angleMemo_.find(mk);
+                    if (it != angleMemo_.end()) {
+                        edgeRows.push_back(it->second);
+                    } else {
+                        auto ins = slotOf.emplace(mk, (int)newKeys.size());
+                        if (ins.second) {
+                            newKeys.push_back(key);
+                            newAngles.push_back(ang);
+                        }
+                        edgeRows.push_back(-(ins.first->second + 1));
                     }
-                    edgeRows.push_back(-(ins.first->second + 1));
+                    prev = cur;
                 }
-                prev = cur;
             }
+            edgeOffsets[p - lo + 1] = (int64_t)edgeRows.size();
         }
-        edgeOffsets[p + 1] = (int64_t)edgeRows.size();
+        readScalars();
+        const int64_t freeRows = h_scalars_[1];
+        if ((int64_t)newKeys.size() <= freeRows) break;
+        if (attempt == 0) {
+            // drop what the range does not use: every integer-keyed row (a population of [id, offset] genes uses none) and the
+            // (edge, offset) entries no plan of the range refers to
+            {
+                std::unordered_map<uint64_t, int> kept;
+                for (int64_t p = lo; p < hi; ++p) {
+                    const int64_t g0 = offsets[p], n = offsets[p + 1] - g0;
+                    if (!active[p] || n <= 0) continue;
+                    int prev = hasStart_ ? N_ : ids[g0];
+                    const int64_t firstEnd = hasStart_ ? 0 : 1, ends = n + (loops_ ? 1 : 0);
+                    for (int64_t k = firstEnd; k < ends; ++k) {
+                        const int64_t gk = k < n ? k : 0;
+                        const uint64_t mk = angle_key(prev * N_ + ids[g0 + gk], angles[g0 + gk]);
+                        auto it = angleMemo_.find(mk);
+                        if (it != angleMemo_.end()) kept.emplace(mk, it->second);
+                        prev = ids[g0 + gk];
+                    }
+                }
+                std::vector<int> freed;
+                for (const auto& kv : angleMemo_)
+                    if (!kept.count(kv.first)) freed.push_back(kv.second);
+                angleMemo_.swap(kept);
+                if (!freed.empty()) {
+                    rowListToDevice(freed);
+                    launch_release_rows(d_rowList_, (int)freed.size(), d_freeStack_, d_scalars_ + 1, stream_);
+                    nLaunches_++;
+                }
+            }
+            launch_fill_u8(d_evictUsed(), nKeys_, 0, stream_);
+            IPP_CUDA_CHECK(cudaMemsetAsync(d_scalars_ + 2, 0, sizeof(int), stream_));
+            launch_gc_rows(d_rowmap_, d_evictUsed_, nKeys_, d_freeStack_, d_scalars_ + 1, d_scalars_ + 2, stream_);
+            nLaunches_ += 2;
+            liveRows_ = readInt(d_scalars_ + 2);
+            headingReversed_.clear();
+            nEvictions_++;
+            continue;
+        }
+        if (pop == 1)
+            throw std::runtime_error("libipp: the edge-bitmap cache (" + std::to_string(rowCapacity_) + " rows) cannot hold the " +
+                                     std::to_string(newKeys.size()) + " edges of a single plan");
+        const int64_t mid = lo + pop / 2;
+        anglesRange(ids, angles, offsets, active, lo, mid, memo, d_ids, d_offsets, d_fitness, wantUnion);
+        anglesRange(ids, angles, offsets, active, mid, hi, memo, d_ids, d_offsets, d_fitness, wantUnion);
+        return;
     }
     const int nNew = (int)newKeys.size();
-    if (nNew > freeRows)
-        throw std::runtime_error("libipp: edge-bitmap cache full (" + std::to_string(nNew) + " new edges, " + std::to_string(freeRows) +
-                                 " free rows); call updateMemoisedEdges or evaluate a smaller batch");
     // render the new pairs, at most nKeys_ at a time (the size of the key and offset staging buffers)
     std::vector<int> newRows(nNew);
     if (nNew > 0 && !d_angleBuf_) d_angleBuf_ = dalloc<float>(nKeys_);
@@ -826,36 +986,26 @@ void Evaluator::evaluatePopulationAngles(const int32_t* ids, const float* angles
     if (nEdges > 0) IPP_CUDA_CHECK(cudaMemcpyAsync(d_edgeRows_, edgeRows.data(), (size_t)nEdges * sizeof(int), cudaMemcpyHostToDevice, stream_));
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_edgeOffsets_, edgeOffsets.data(), (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
     PlanReduceArgs rd;
-    rd.ids = d_ids_; rd.offsets = d_offsets_; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
-    rd.active = d_active_; rd.rowmap = d_rowmap_; rd.edgeRows = d_edgeRows_; rd.edgeOffsets = d_edgeOffsets_;
+    rd.ids = d_ids; rd.offsets = d_offsets + lo; rd.pop = pop; rd.N = N_; rd.hasStart = hasStart_; rd.loops = loops_;
+    rd.active = d_active_ + lo; rd.rowmap = d_rowmap_; rd.edgeRows = d_edgeRows_; rd.edgeOffsets = d_edgeOffsets_;
     rd.rows = d_rows_; rd.rowWords = rowWords_; rd.area = scene_.area;
-    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness_; rd.partial = reducePartials(pop);
+    rd.nTiles = nTiles_; rd.totalArea = totalArea_; rd.fitness = d_fitness + 4 * lo; rd.partial = reducePartials(pop);
     groupBegin(KG_REDUCE);
     launch_plan_reduce(rd, numSMs_, stream_);
     groupEnd(KG_REDUCE);
     nLaunches_++;
     nReduceLaunches_++;
     nPlansReduced_ += pop;
-    IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, d_fitness_, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
 
-    auto rowListToDevice = [&](const std::vector<int>& list) {
-        if ((int64_t)list.size() > rowListCap_) {
-            cudaFree(d_rowList_);
-            rowListCap_ = (int64_t)list.size() + (int64_t)list.size() / 4 + 16;
-            d_rowList_ = dalloc<int>(rowListCap_);
-        }
-        if (!list.empty()) IPP_CUDA_CHECK(cudaMemcpyAsync(d_rowList_, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    };
-    if (unionBitmap) {
+    if (wantUnion) {
         std::vector<int> uniq(edgeRows);
         std::sort(uniq.begin(), uniq.end());
         uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
         rowListToDevice(uniq);
         launch_union_row_list(d_rowList_, (int)uniq.size(), d_rows_, rowWords_, d_union_, stream_);
         nLaunches_++;
-        IPP_CUDA_CHECK(cudaMemcpyAsync(unionBitmap, d_union_, (size_t)bitmapWords() * 4, cudaMemcpyDeviceToHost, stream_));
     }
-    sync();
+    sync();  // (the host vectors above feed asynchronous copies)
     if (memo) {
         for (const auto& kv : slotOf) angleMemo_[kv.first] = newRows[kv.second];
     } else if (nNew > 0) {
@@ -911,8 +1061,9 @@ void Evaluator::evaluatePopulationHost(const int32_t* ids, const float* angles, 
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_ids_, ids, (size_t)nGenes * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
     IPP_CUDA_CHECK(cudaMemcpyAsync(d_offsets_, offsets, (size_t)(pop + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, stream_));
     if (angles) {
-        requireQuickHeading();
-        evaluatePopulationAngles(ids, angles, offsets, pop, memo, noLimit, fitness, unionBitmap);
+        evaluatePopulationAngles(ids, angles, offsets, pop, memo, noLimit, d_ids_, d_offsets_, d_fitness_, unionBitmap);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(fitness, d_fitness_, (size_t)pop * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+        sync();
         return;
     }
     evaluatePopulationDevice(d_ids_, nullptr, d_offsets_, pop, nGenes, memo, noLimit, d_fitness_, unionBitmap);
@@ -962,7 +1113,7 @@ void Evaluator::renderKeysHeadingSearch(const int* d_keys, int nNew) {
     if (nNew <= 0) return;
     if (!d_sortedKeys_) d_sortedKeys_ = dalloc<int>(nKeys_);
     if (!d_angleBuf_) d_angleBuf_ = dalloc<float>(nKeys_);
-    const int chunkMax = std::max(1, std::min(nKeys_ / 2, batchCap_));
+    const int chunkMax = headingChunk();
     std::vector<int> keys(nNew);
     IPP_CUDA_CHECK(cudaMemcpyAsync(keys.data(), d_keys, (size_t)nNew * sizeof(int), cudaMemcpyDeviceToHost, stream_));
     sync();

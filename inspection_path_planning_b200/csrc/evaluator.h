@@ -51,6 +51,7 @@ class Evaluator {
     int64_t renderEdgesShared(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, Collectives& cx);
     int64_t updateMemoisedEdges(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
     int64_t memoSize() const { return liveRows_ + (int64_t)angleMemo_.size(); }
+    int64_t evictions() const { return nEvictions_; }  // times the row pool ran full and rows of unused edges were dropped
     void clearMemo();
     void interpretPlan(const double* genes, int n, int width, double* pos, double* dirs, int* nPos, int* nDirs);
 
@@ -69,7 +70,7 @@ class Evaluator {
     double timerStop();
     void flushL2();
     void counters(int64_t out[8], bool reset);
-    void visibilityStats(int64_t out[6], bool reset);
+    void visibilityStats(int64_t out[8], bool reset);
     void kernelTime(int which, double* ms, int64_t* launches, bool reset);
     void setProfiling(bool on) { profiling_ = on; }
     bool usesBins() const { return useBins_; }
@@ -93,8 +94,14 @@ class Evaluator {
     void renderNewEdges(int nNew, const float* d_angles);
     void renderKeys(const int* d_keys, int n, const float* d_angles, bool publish = true, std::vector<int>* rowsOut = nullptr);
     void energyAndGate(const int32_t* d_ids, const int64_t* d_offsets, int64_t pop, bool noLimit, double* d_fitness);
+    void coverageRange(const int32_t* d_ids, const int64_t* d_offsets, int64_t lo, int64_t hi, bool memo, double* d_fitness, bool wantUnion);
+    int headingChunk() const;
+    uint8_t* d_evictUsed();
     void evaluatePopulationAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop, bool memo, bool noLimit,
-                                  double* fitness, uint32_t* unionBitmap);
+                                  const int32_t* d_ids, const int64_t* d_offsets, double* d_fitness, uint32_t* unionBitmap);
+    void anglesRange(const int32_t* ids, const float* angles, const int64_t* offsets, const uint8_t* active, int64_t lo, int64_t hi, bool memo,
+                     const int32_t* d_ids, const int64_t* d_offsets, double* d_fitness, bool wantUnion);
+    void rowListToDevice(const std::vector<int>& list);
     int64_t updateMemoisedEdgesAngles(const int32_t* ids, const float* angles, const int64_t* offsets, int64_t pop);
     void renderBatch(const int* d_keys, const float* d_angles, int n, const int* d_rowOfSlot);
     void renderSnapshots(int nSnaps, int32_t* d_idImage);
@@ -125,6 +132,7 @@ class Evaluator {
     uint8_t* d_coll_ = nullptr;    // nKeys (padded to 4)
     int* d_rowmap_ = nullptr;      // nKeys
     uint8_t* d_used_ = nullptr;    // nKeys
+    uint8_t* d_evictUsed_ = nullptr;  // nKeys, made on the first eviction
     int* d_newKeys_ = nullptr;     // nKeys
     int* d_scalars_ = nullptr;     // [0] newCount, [1] freeTop, [2] live, [3] scratch
     int* h_scalars_ = nullptr;     // pinned mirror
@@ -143,7 +151,7 @@ class Evaluator {
     int64_t snapCap_ = 0;
     void* d_scanTmp_ = nullptr;
     size_t scanTmpBytes_ = 0;
-    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] work cursor, [2] nodes fetched, [3] triangles staged, [4] tiles, [5] bin entries read
+    unsigned long long* d_visCounters_ = nullptr;  // [0] rays, [1] work cursor, [2] nodes fetched, [3] triangles staged, [4] tiles, [5] bin entries read, [6..7] diagnostics, [8] supertiles from records, [9] supertiles by leaf walk
     // leaf-bin variant of K4 (visibility_bins.cu)
     bool useBins_ = false;
     BinBuffers bins_;
@@ -175,6 +183,7 @@ class Evaluator {
     double* d_fitShared_ = nullptr;
     int64_t sharedCap_ = 0;
     int64_t maxSnapsPerBatch_ = 1 << 20;
+    bool memoDiverged_ = false;  // the shared rendering was skipped once: the ranks' memos may differ, the next shared call clears them
     float* d_angleOne_ = nullptr;
 
     // plan buffers (host-pointer entry point)
@@ -196,7 +205,7 @@ class Evaluator {
     int64_t flushWords_ = 0;
     // counters
     int64_t nLaunches_ = 0, nSnapshots_ = 0, nEdgesRendered_ = 0, nCollisionQueries_ = 0, nReduceLaunches_ = 0, nPlansReduced_ = 0,
-            nRowsRead_ = 0;
+            nRowsRead_ = 0, nEvictions_ = 0;
 };
 
 

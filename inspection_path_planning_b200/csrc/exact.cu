@@ -346,11 +346,13 @@ __global__ void k_mark_collisions(PlanMarkArgs a) {
     if (p >= a.pop) return;
     PlanIter it{a.ids, a.offsets[p], a.offsets[p + 1], a.N, a.hasStart, a.loops, 0};
     int m = it.count();
+    // box ids are checked before anything is claimed (assert at PlanInterpreterBoxOrder.cpp:282): a plan with a bad id claims
+    // nothing, and the host resolves what the other plans claimed before it reports the error -- no flag is left pending
+    for (int64_t g = a.offsets[p]; g < a.offsets[p + 1]; ++g)
+        if ((unsigned)a.ids[g] >= (unsigned)a.N) { *a.errFlag = 1; return; }
     int prev = m > 0 ? it.at(0) : 0;
-    if (m > 0 && (unsigned)prev >= (unsigned)(a.N + (a.hasStart ? 1 : 0))) { *a.errFlag = 1; return; }
     for (int k = 1; k < m; ++k) {
         int cur = it.at(k);
-        if ((unsigned)cur >= (unsigned)a.N) { *a.errFlag = 1; return; }
         int key = prev * a.N + cur;
         if (a.coll[key] == 0xFF) {
             // claim: 0xFF unknown -> 0xFE pending (byte CAS through the containing word)
@@ -471,6 +473,7 @@ __global__ void k_gc_rows(int* __restrict__ rowmap, const uint8_t* __restrict__ 
     int key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= nKeys) return;
     int r = rowmap[key];
+    if (r == -2) rowmap[key] = -1;  // a claim that was never published (defensive: failed calls roll their claims back themselves)
     if (r < 0) return;
     if (used[key]) {
         atomicAdd(live, 1);
@@ -486,14 +489,41 @@ void launch_gc_rows(int* d_rowmap, const uint8_t* d_used, int nKeys, int* d_free
 
 // rows for freshly claimed keys: pop from the free stack
 __global__ void k_assign_rows(const int* __restrict__ keys, int n, int* __restrict__ rowmapPending, int* __restrict__ rowsOut,
-                              const int* __restrict__ freeStack, int* __restrict__ freeTop) {
+                              const int* __restrict__ freeStack, int* __restrict__ freeTop, int scratchRow, int* __restrict__ errFlag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int t = atomicSub(freeTop, 1) - 1;
+    if (t < 0) {  // the caller checks the capacity first; never index below the stack: render into the scratch row and report
+        atomicAdd(freeTop, 1);
+        *errFlag = 2;
+        rowsOut[i] = scratchRow;
+        return;
+    }
     rowsOut[i] = freeStack[t];
 }
-void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, cudaStream_t st) {
-    if (n > 0) k_assign_rows<<<(n + 255) / 256, 256, 0, st>>>(d_keys, n, d_rowmap, d_rowsOut, d_freeStack, d_freeTop);
+void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, int scratchRow,
+                        int* d_errFlag, cudaStream_t st) {
+    if (n > 0) k_assign_rows<<<(n + 255) / 256, 256, 0, st>>>(d_keys, n, d_rowmap, d_rowsOut, d_freeStack, d_freeTop, scratchRow, d_errFlag);
+}
+// claims that will not be rendered after all (the call failed or is retried in smaller pieces): pending -> unknown
+__global__ void k_unclaim_rows(const int* __restrict__ keys, int n, int* __restrict__ rowmap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && rowmap[keys[i]] == -2) rowmap[keys[i]] = -1;
+}
+void launch_unclaim_rows(const int* d_keys, int n, int* d_rowmap, cudaStream_t st) {
+    if (n > 0) k_unclaim_rows<<<(n + 255) / 256, 256, 0, st>>>(d_keys, n, d_rowmap);
+}
+// memoization == false: the rows rendered for this call go straight back to the free stack
+__global__ void k_unpublish_rows(const int* __restrict__ keys, int n, int* __restrict__ rowmap, int* __restrict__ freeStack,
+                                 int* __restrict__ freeTop) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = rowmap[keys[i]];
+    rowmap[keys[i]] = -1;
+    if (r >= 0) freeStack[atomicAdd(freeTop, 1)] = r;
+}
+void launch_unpublish_rows(const int* d_keys, int n, int* d_rowmap, int* d_freeStack, int* d_freeTop, cudaStream_t st) {
+    if (n > 0) k_unpublish_rows<<<(n + 255) / 256, 256, 0, st>>>(d_keys, n, d_rowmap, d_freeStack, d_freeTop);
 }
 __global__ void k_publish_rows(const int* __restrict__ keys, const int* __restrict__ rows, int n, int* __restrict__ rowmap) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -162,6 +162,7 @@ int ipp_update_memoised_edges(ipp_t* h, const int32_t* ids, const float* angles,
     IPP_CATCH
 }
 int64_t ipp_memo_size(const ipp_t* h) { return E(h).memoSize(); }
+int64_t ipp_evictions(const ipp_t* h) { return E(h).evictions(); }
 int ipp_clear_memo(ipp_t* h) {
     IPP_TRY
     E(h).clearMemo();
@@ -268,9 +269,9 @@ int ipp_counters(ipp_t* h, int64_t* out8, int reset) {
     E(h).counters(out8, reset != 0);
     IPP_CATCH
 }
-int ipp_visibility_stats(ipp_t* h, int64_t* out6, int reset) {
+int ipp_visibility_stats(ipp_t* h, int64_t* out8, int reset) {
     IPP_TRY
-    E(h).visibilityStats(out6, reset != 0);
+    E(h).visibilityStats(out8, reset != 0);
     IPP_CATCH
 }
 int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,

@@ -71,7 +71,10 @@ void launch_mark_rows(const PlanMarkArgs& a, cudaStream_t st);
 // counts (into a.newCount) the edges of the active plans that have no bitmap row yet, without claiming them
 void launch_probe_rows(const PlanMarkArgs& a, cudaStream_t st);
 void launch_gc_rows(int* d_rowmap, const uint8_t* d_used, int nKeys, int* d_freeStack, int* d_freeTop, int* d_live, cudaStream_t st);
-void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, cudaStream_t st);
+void launch_assign_rows(const int* d_keys, int n, int* d_rowmap, int* d_rowsOut, const int* d_freeStack, int* d_freeTop, int scratchRow,
+                        int* d_errFlag, cudaStream_t st);
+void launch_unclaim_rows(const int* d_keys, int n, int* d_rowmap, cudaStream_t st);
+void launch_unpublish_rows(const int* d_keys, int n, int* d_rowmap, int* d_freeStack, int* d_freeTop, cudaStream_t st);
 void launch_publish_rows(const int* d_keys, const int* d_rows, int n, int* d_rowmap, cudaStream_t st);
 // bitmap rows of n keys <-> a contiguous staging buffer (n x rowWords), for the exchange of freshly rendered rows between ranks
 void launch_rows_gather(const int* d_keys, int n, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_out, cudaStream_t st);

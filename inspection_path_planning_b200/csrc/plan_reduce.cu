@@ -287,7 +287,7 @@ __global__ void k_union_rows(const uint8_t* __restrict__ used, int nKeys, const 
         int r = rowmap[k];
         if (r >= 0) acc |= rows[(size_t)r * rowWords + w];
     }
-    out[w] = acc;
+    out[w] |= acc;  // accumulated: a population evaluated in several pieces adds the union of each piece
 }
 
 __global__ void k_union_row_list(const int* __restrict__ rowList, int n, const uint32_t* __restrict__ rows, long long rowWords,
@@ -296,7 +296,7 @@ __global__ void k_union_row_list(const int* __restrict__ rowList, int n, const u
     if (w >= rowWords) return;
     uint32_t acc = 0;
     for (int k = 0; k < n; ++k) acc |= rows[(size_t)rowList[k] * rowWords + w];
-    out[w] = acc;
+    out[w] |= acc;  // accumulated, like k_union_rows
 }
 __global__ void k_release_rows(const int* __restrict__ rowList, int n, int* __restrict__ freeStack, int* __restrict__ freeTop) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

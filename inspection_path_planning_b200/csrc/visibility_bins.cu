@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     unsigned* hdr = reinterpret_cast<unsigned*>(rec + (size_t)(kBinRecords + 32) * 4);  // one word per record: leaf depth key:16 | tiles:16
     uint16_t* q16 = reinterpret_cast<uint16_t*>(S.queue);                                // phase 2: records waiting for a staging round
     unsigned long long myRays = 0, myEntries = 0;
-    unsigned myTris = 0, myTiles = 0;  // statistics (lane 0 only matters)
+    unsigned myTris = 0, myTiles = 0, mySuperRec = 0, mySuperWalk = 0;  // statistics (lane 0 only matters)
 #ifdef IPP_VIS_DIAG
     unsigned myLive = 0, myOpen = 0, myOpenTris = 0;
 #endif
@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
             for (int d = 16; d; d >>= 1) nRec += __shfl_xor_sync(0xffffffffu, nRec, d);
             cached = nRec <= kBinRecords;
         }
+        if (cached) mySuperRec++;
+        else mySuperWalk++;
         if (cached) {
             TileGeom none = {};
             SuperGeom sgm;
@@ -497,6 +499,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         atomicAdd(&counters[3], (unsigned long long)myTris);
         atomicAdd(&counters[4], (unsigned long long)myTiles);
         atomicAdd(&counters[5], myEntries);
+        atomicAdd(&counters[8], (unsigned long long)mySuperRec);
+        atomicAdd(&counters[9], (unsigned long long)mySuperWalk);
 #ifdef IPP_VIS_DIAG
         atomicAdd(&counters[6], (unsigned long long)myLive);
         atomicAdd(&counters[7], (unsigned long long)myOpen);

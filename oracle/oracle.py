@@ -79,6 +79,8 @@ class Oracle:
             raise ValueError(L.oracle_last_error().decode())
         self._h = h
         self._L = L
+        self.has_start = start is not None
+        self.loops = bool(plan_loops_around)
         self.T = int(L.oracle_num_triangles(h))
         self.W32 = (self.T + 31) // 32
 
