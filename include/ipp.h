@@ -111,6 +111,10 @@ int64_t ipp_memo_size(const ipp_t* h);
  * call does not use are dropped, and a population that still needs more rows than the pool holds is evaluated in pieces; results
  * never depend on what was cached.  This returns how often rows were dropped that way since the evaluator was made. */
 int64_t ipp_evictions(const ipp_t* h);
+/* Chooses the streaming kernel of the plan reduce (K6) for A/B measurements, process wide: -1 = the library's choice, 0 = plain
+ * vector loads, 1.. = configurations of the bulk-asynchronous-copy kernel.  Returns a description of the variant.  Every variant
+ * returns the same bits. */
+const char* ipp_plan_reduce_variant(int v);
 /* drop all memoised edges and collision flags */
 int ipp_clear_memo(ipp_t* h);
 
@@ -129,10 +133,11 @@ int ipp_edges_collide(ipp_t* h, const double* edges_nx6, int64_t n, uint8_t* out
 int ipp_boxes_hit_mesh(ipp_t* h, const double* centres_nx3, int64_t n, double half_side, uint8_t* out_flags);
 /* one camera pose -> per-pixel nearest triangle id (-1 background), row-major [y][x] */
 int ipp_render_ids(ipp_t* h, const double* eye3, const double* center3, const double* up3, int32_t* out_HxW);
-/* the depth-sorted leaf table the binned visibility kernel builds for one camera pose: up to cap packed entries
- * [depth:16 | tx0:5 tx1:5 ty0:5 ty1:5 | first triangle:24 count:4], *count = entries of the pose, out_tile_mask32 = occupied tiles */
+/* the depth-sorted cluster table the binned visibility kernel builds for one camera pose: up to cap packed entries
+ * [depth:16 | tx0:5 tx1:5 ty0:5 ty1:5 | cluster:28], *count = entries of the pose, out_tile_mask32 = occupied tiles; out_first /
+ * out_count (nullable, cap entries): the run of BVH-ordered triangles each entry's cluster stands for */
 int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,
-                   uint32_t* out_tile_mask32);
+                   uint32_t* out_tile_mask32, int32_t* out_first, int32_t* out_count);
 /* triangle id (file order) at every position of the BVH-ordered triangle arrays: out_T[position] = id */
 int ipp_bvh_order(ipp_t* h, int32_t* out_T);
 /* BVH self-check: closest-hit of n rays (origin xyz, dir xyz) through the BVH and by brute force; returns
@@ -155,6 +160,10 @@ int ipp_timer_start(ipp_t* h);
 int ipp_timer_stop(ipp_t* h, double* ms);
 /* overwrite a buffer larger than L2 */
 int ipp_flush_l2(ipp_t* h);
+/* measured read bandwidth (GB/s) of `bytes` bytes (at most 256 MiB) read `reps` times with plain 16-byte loads by a grid over all
+ * SMs: a size inside L2 gives the L2 read peak bench.py sets the visibility kernel's lts__t_bytes rate against, a size beyond it
+ * the HBM read peak */
+int ipp_read_bandwidth(ipp_t* h, int64_t bytes, int reps, double* gbs);
 /* counters since the last reset: [0] kernel launches, [1] pixel-centre rays issued, [2] snapshots rendered,
  * [3] edges rendered, [4] collision queries, [5] plan_reduce launches, [6] plans reduced, [7] bitmap rows read */
 int ipp_counters(ipp_t* h, int64_t* out8, int reset);
@@ -163,8 +172,8 @@ int ipp_counters(ipp_t* h, int64_t* out8, int reset);
  * binned variant), [1] triangles staged (48 B each), [2] 32x32-pixel tiles rasterised, [3] pixel-centre rays, and, only when the
  * library was built with -DIPP_VIS_DIAG (they cost 2 % of the kernel; 0 otherwise), for the binned variant [4] staged triangles that
  * survived set-up (can produce a fragment in their tile), [5] tiles in which some ray never hit, so that the leaf list was walked
- * to its end; binned variant, always: [6] 128x128 supertiles rasterised from cached set-up records (the path the 1024-pixel
- * configurations take), [7] supertiles whose triangle list overflowed the record scratch and took the leaf walk */
+ * to its end; binned variant, always: [6] 128x128 supertiles rasterised, [7] how often a supertile (or a part of one) held more
+ * triangles than the record scratch of its warp and was split into halves */
 int ipp_visibility_stats(ipp_t* h, int64_t* out8, int reset);
 /* which edge-visibility kernel renders the item buffers: 1 = depth-sorted leaf bins per 128x128 supertile (the default when the
  * mesh has <= 16384 BVH leaves and the image is <= 1024 pixels a side), 0 = BVH frustum walk per tile.  Same sampling rule and

@@ -39,13 +39,14 @@ PROTOTYPES = {
     "ipp_update_memoised_edges": (C.c_int, [H, c_i32p, c_f32p, c_i64p, C.c_int64, c_i64p]),
     "ipp_memo_size": (C.c_int64, [H]),
     "ipp_evictions": (C.c_int64, [H]),
+    "ipp_plan_reduce_variant": (C.c_char_p, [C.c_int]),
     "ipp_clear_memo": (C.c_int, [H]),
     "ipp_interpret_plan": (C.c_int, [H, c_f64p, C.c_int, C.c_int, c_f64p, c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ipp_edge_bitmap": (C.c_int, [H, C.c_int, C.c_int, C.c_double, c_u32p]),
     "ipp_edges_collide": (C.c_int, [H, c_f64p, C.c_int64, c_u8p]),
     "ipp_boxes_hit_mesh": (C.c_int, [H, c_f64p, C.c_int64, C.c_double, c_u8p]),
     "ipp_render_ids": (C.c_int, [H, c_f64p, c_f64p, c_f64p, c_i32p]),
-    "ipp_leaf_table": (C.c_int, [H, c_f64p, c_f64p, c_f64p, C.POINTER(C.c_uint64), C.c_int64, c_i64p, c_u32p]),
+    "ipp_leaf_table": (C.c_int, [H, c_f64p, c_f64p, c_f64p, C.POINTER(C.c_uint64), C.c_int64, c_i64p, c_u32p, c_i32p, c_i32p]),
     "ipp_bvh_order": (C.c_int, [H, c_i32p]),
     "ipp_bvh_selftest": (C.c_int, [H, c_f32p, C.c_int64, c_i32p, c_i64p]),
     "ipp_bvh_selftest_ex": (C.c_int, [H, c_f32p, C.c_int64, c_i32p, c_i32p, c_f32p, c_i64p]),
@@ -59,6 +60,7 @@ PROTOTYPES = {
     "ipp_timer_start": (C.c_int, [H]),
     "ipp_timer_stop": (C.c_int, [H, c_f64p]),
     "ipp_flush_l2": (C.c_int, [H]),
+    "ipp_read_bandwidth": (C.c_int, [H, C.c_int64, C.c_int, c_f64p]),
     "ipp_counters": (C.c_int, [H, c_i64p, C.c_int]),
     "ipp_visibility_stats": (C.c_int, [H, c_i64p, C.c_int]),
     "ipp_visibility_variant": (C.c_int, [H, C.c_int, C.POINTER(C.c_int)]),

@@ -363,13 +363,17 @@ class PlanCoverageEstimator(object):
         out = np.zeros(cap, dtype=np.uint64)
         mask = np.zeros(32, dtype=np.uint32)
         n = C.c_int64()
+        first = np.zeros(cap, dtype=np.int32)
+        cnt = np.zeros(cap, dtype=np.int32)
         _lib.check(self._L.ipp_leaf_table(self._h, e.ctypes.data_as(_lib.c_f64p), c.ctypes.data_as(_lib.c_f64p), u.ctypes.data_as(_lib.c_f64p),
-                                          out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n), mask.ctypes.data_as(_lib.c_u32p)))
-        k = out[:min(int(n.value), cap)]
+                                          out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n), mask.ctypes.data_as(_lib.c_u32p),
+                                          first.ctypes.data_as(_lib.c_i32p), cnt.ctypes.data_as(_lib.c_i32p)))
+        m = min(int(n.value), cap)
+        k = out[:m]
         return {"count": int(n.value), "zq": (k >> np.uint64(48)).astype(np.int64), "tx0": ((k >> np.uint64(43)) & np.uint64(31)).astype(np.int64),
                 "tx1": ((k >> np.uint64(38)) & np.uint64(31)).astype(np.int64), "ty0": ((k >> np.uint64(33)) & np.uint64(31)).astype(np.int64),
-                "ty1": ((k >> np.uint64(28)) & np.uint64(31)).astype(np.int64), "first": ((k >> np.uint64(4)) & np.uint64(0xFFFFFF)).astype(np.int64),
-                "cnt": (k & np.uint64(15)).astype(np.int64), "tile_mask": mask}
+                "ty1": ((k >> np.uint64(28)) & np.uint64(31)).astype(np.int64), "first": first[:m].astype(np.int64),
+                "cnt": cnt[:m].astype(np.int64), "tile_mask": mask}
 
     def bvh_order(self):
         """Triangle id (file order) at every position of the BVH-ordered triangle arrays."""
@@ -400,7 +404,7 @@ class PlanCoverageEstimator(object):
     def visibility_stats(self, reset=False):
         out = np.zeros(8, dtype=np.int64)
         _lib.check(self._L.ipp_visibility_stats(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
-        return dict(zip(["nodes", "triangles", "tiles", "rays", "live_triangles", "open_tiles", "supertiles_records", "supertiles_leaf_walk"],
+        return dict(zip(["nodes", "triangles", "tiles", "rays", "live_triangles", "open_tiles", "supertiles", "supertile_splits"],
                         (int(x) for x in out)))
 
     def visibility_variant(self, use_bins=None):

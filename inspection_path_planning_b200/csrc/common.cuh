@@ -32,6 +32,8 @@ constexpr double kCameraFarPlaneDist = 10.0;
 constexpr int kLeafMax = 8;          // triangles per BVH leaf
 constexpr int kLeafShift = 4;        // leaf link: ~link = (first << kLeafShift) | count
 constexpr int kLeafMask = 15;
+constexpr int kMaxBinLeaves = 16384;    // clusters a camera pose can sort (visibility_bins.cu)
+constexpr int kMaxClusterTris = 128;    // largest cluster of the binned visibility kernel
 constexpr int kMaxDepth = 96;        // Karras tree over 63-bit Morton codes + 31-bit index tie-break: depth <= 96
 constexpr int kTileWords = 128;      // bitmap words per plan_reduce tile (one uint4 per lane)
 constexpr int kTileTris = kTileWords * 32;
@@ -54,9 +56,10 @@ struct DeviceScene {
     // BVH-ordered triangles, file vertex order (exact collision predicate); a.w = original id
     float4 *oa = nullptr, *ob = nullptr, *oc = nullptr;
     BvhNode* nodes = nullptr;
-    // the leaves of the BVH as a flat table (node order = Morton order): padded box, leafLo.w = (first << kLeafShift) | count as int bits
+    // cluster table of the binned visibility kernel: maximal BVH subtrees of at most leafCap triangles (leafCap = kLeafMax: the leaves
+    // of the node array), node order.  Padded box; leafLo.w = first triangle (BVH order), leafHi.w = count, both as int bits
     float4 *leafLo = nullptr, *leafHi = nullptr;
-    int nLeaves = 0;
+    int nLeaves = 0, leafCap = 0;
     double* area = nullptr;   // [areaPad] file order, zero padded to a multiple of kTileTris
     float bbmin[3], bbmax[3]; // float bounding box of all vertices
 };

@@ -334,6 +334,29 @@ void Evaluator::flushL2() {
     nLaunches_++;
 }
 
+// Measured read bandwidth of a buffer of `bytes` bytes read `reps` times by every SM (GB/s): a buffer well inside L2 (e.g. 32 MiB)
+// gives the L2 read peak this box reaches with plain 16-byte loads, one larger than L2 the HBM read peak.
+double Evaluator::readBandwidth(int64_t bytes, int reps) {
+    bind();
+    if (!d_flushBuf_) flushL2();
+    const int64_t words = std::min<int64_t>(flushWords_, std::max<int64_t>(bytes / 4, 1024));
+    unsigned* d_sink = reinterpret_cast<unsigned*>(d_scalars_ + 7);
+    launch_read_probe(d_flushBuf_, words, 2, d_sink, numSMs_, stream_);  // warm: the buffer is in L2 if it fits
+    cudaEvent_t a, b;
+    IPP_CUDA_CHECK(cudaEventCreate(&a));
+    IPP_CUDA_CHECK(cudaEventCreate(&b));
+    IPP_CUDA_CHECK(cudaEventRecord(a, stream_));
+    launch_read_probe(d_flushBuf_, words, reps, d_sink, numSMs_, stream_);
+    IPP_CUDA_CHECK(cudaEventRecord(b, stream_));
+    IPP_CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    IPP_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    nLaunches_ += 2;
+    return ms > 0 ? (double)words * 4.0 * reps / (ms * 1e-3) / 1e9 : 0.0;
+}
+
 void Evaluator::exclusiveScan(const int* d_in, int* d_out, int n) {
     size_t need = scan_tmp_bytes(n);
     if (need > scanTmpBytes_) {
@@ -1314,7 +1337,7 @@ void Evaluator::renderIds(const double* eye, const double* center, const double*
 }
 
 void Evaluator::leafTable(const double* eye, const double* center, const double* up, uint64_t* out, int64_t cap, int64_t* count,
-                          uint32_t* mask32) {
+                          uint32_t* mask32, int32_t* outFirst, int32_t* outCount) {
     bind();
     if (!useBins_) throw std::logic_error("libipp: the leaf-bin variant is not in force for this evaluator");
     ensureSnapBuffers(2);
@@ -1327,6 +1350,17 @@ void Evaluator::leafTable(const double* eye, const double* center, const double*
     if (m > 0) IPP_CUDA_CHECK(cudaMemcpyAsync(out, bins_.table, (size_t)m * 8, cudaMemcpyDeviceToHost, stream_));
     if (mask32) IPP_CUDA_CHECK(cudaMemcpyAsync(mask32, bins_.tileMask, 32 * 4, cudaMemcpyDeviceToHost, stream_));
     sync();
+    if (outFirst || outCount) {  // the triangles of every entry's cluster (the entry carries the cluster index)
+        std::vector<float4> lo(scene_.nLeaves), hi(scene_.nLeaves);
+        IPP_CUDA_CHECK(cudaMemcpyAsync(lo.data(), scene_.leafLo, lo.size() * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
+        IPP_CUDA_CHECK(cudaMemcpyAsync(hi.data(), scene_.leafHi, hi.size() * sizeof(float4), cudaMemcpyDeviceToHost, stream_));
+        sync();
+        for (int64_t k = 0; k < m; ++k) {
+            const uint32_t ref = (uint32_t)(out[k] & 0x0fffffffu);
+            if (outFirst) memcpy(outFirst + k, &lo[ref].w, 4);
+            if (outCount) memcpy(outCount + k, &hi[ref].w, 4);
+        }
+    }
 }
 
 void Evaluator::bvhOrder(int32_t* out) {

@@ -60,7 +60,8 @@ class Evaluator {
     void edgesCollide(const double* edges, int64_t n, uint8_t* out);
     void boxesHitMesh(const double* centres, int64_t n, double half, uint8_t* out);
     void renderIds(const double* eye, const double* center, const double* up, int32_t* out);
-    void leafTable(const double* eye, const double* center, const double* up, uint64_t* out, int64_t cap, int64_t* count, uint32_t* mask32);
+    void leafTable(const double* eye, const double* center, const double* up, uint64_t* out, int64_t cap, int64_t* count, uint32_t* mask32,
+                   int32_t* outFirst = nullptr, int32_t* outCount = nullptr);
     void bvhOrder(int32_t* out);
     void bvhSelftest(const float* rays, int64_t n, int32_t* outIds, int64_t* mismatches, int32_t* outBrute = nullptr, float* outT = nullptr);
 
@@ -69,6 +70,7 @@ class Evaluator {
     void timerStart();
     double timerStop();
     void flushL2();
+    double readBandwidth(int64_t bytes, int reps);
     void counters(int64_t out[8], bool reset);
     void visibilityStats(int64_t out[8], bool reset);
     void kernelTime(int which, double* ms, int64_t* launches, bool reset);

@@ -163,6 +163,15 @@ int ipp_update_memoised_edges(ipp_t* h, const int32_t* ids, const float* angles,
 }
 int64_t ipp_memo_size(const ipp_t* h) { return E(h).memoSize(); }
 int64_t ipp_evictions(const ipp_t* h) { return E(h).evictions(); }
+int ipp_read_bandwidth(ipp_t* h, int64_t bytes, int reps, double* gbs) {
+    IPP_TRY
+    *gbs = E(h).readBandwidth(bytes, reps);
+    IPP_CATCH
+}
+const char* ipp_plan_reduce_variant(int v) {
+    ipp::set_plan_reduce_variant(v);
+    return ipp::plan_reduce_variant_name(v);
+}
 int ipp_clear_memo(ipp_t* h) {
     IPP_TRY
     E(h).clearMemo();
@@ -275,9 +284,9 @@ int ipp_visibility_stats(ipp_t* h, int64_t* out8, int reset) {
     IPP_CATCH
 }
 int ipp_leaf_table(ipp_t* h, const double* eye3, const double* center3, const double* up3, uint64_t* out, int64_t cap, int64_t* count,
-                   uint32_t* out_tile_mask32) {
+                   uint32_t* out_tile_mask32, int32_t* out_first, int32_t* out_count) {
     IPP_TRY
-    E(h).leafTable(eye3, center3, up3, out, cap, count, out_tile_mask32);
+    E(h).leafTable(eye3, center3, up3, out, cap, count, out_tile_mask32, out_first, out_count);
     IPP_CATCH
 }
 int ipp_bvh_order(ipp_t* h, int32_t* out_T) {

@@ -99,7 +99,6 @@ void launch_bvh_selftest(const DeviceScene& sc, const float* d_rays, int64_t n, 
 int visibility_grid_blocks();
 
 // visibility_bins.cu -- the same sampling with depth-sorted leaf bins (meshes of <= kMaxBinLeaves leaves, images <= 1024 a side)
-constexpr int kMaxBinLeaves = 16384;
 struct BinBuffers {
     unsigned long long* table = nullptr;      // [poses][stride] packed leaf entries, front to back
     int* tableCount = nullptr;                // [poses] entries per pose
@@ -129,6 +128,9 @@ void exclusive_scan_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t 
 
 // plan_reduce.cu (-fmad=false)
 void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st);
+// which streaming kernel serves ordinary populations: -1 = the library's choice, 0 = plain loads, 1.. = bulk-copy configurations
+void set_plan_reduce_variant(int v);
+const char* plan_reduce_variant_name(int v);
 void launch_union_rows(const uint8_t* d_used, int nKeys, const int* d_rowmap, const uint32_t* d_rows, int64_t rowWords, uint32_t* d_union,
                        cudaStream_t st);
 // OR of an explicit list of rows -> union bitmap; rows back to the free stack
@@ -138,5 +140,6 @@ void launch_fill_u8(uint8_t* p, int64_t n, uint8_t v, cudaStream_t st);
 void launch_fill_i32(int* p, int64_t n, int v, cudaStream_t st);
 void launch_iota_i32(int* p, int64_t n, cudaStream_t st);
 void launch_flush(uint32_t* p, int64_t nWords, cudaStream_t st);
+void launch_read_probe(const uint32_t* p, int64_t nWords, int reps, unsigned* d_sink, int numSMs, cudaStream_t st);
 
 }  // namespace ipp

@@ -134,35 +134,49 @@ __global__ void k_emit(int n, const int* __restrict__ left, const int* __restric
     out[i] = nd;
 }
 
-// Leaf table: the leaf children of the live nodes (nodes inside a collapsed subtree are unreachable).
-__global__ void k_leaf_count(int n, const int* __restrict__ rlo, const int* __restrict__ rhi, const BvhNode* __restrict__ nodes,
-                             int* __restrict__ counts) {
+// Cluster table of the binned visibility kernel: the maximal subtrees of at most C triangles (C = kLeafMax: exactly the leaves of
+// the node array above; larger C for meshes with more leaves than a camera pose can sort), each a contiguous run of the
+// BVH-ordered triangle arrays.  Clusters are the children of the nodes that hold more than C triangles (and of the root).
+__device__ __forceinline__ bool cluster_child(int link, int C, const int* __restrict__ rlo, const int* __restrict__ rhi, int& first, int& cnt) {
+    if (link < 0) {  // a single triangle
+        first = link & 0x7fffffff;
+        cnt = 1;
+        return true;
+    }
+    first = rlo[link];
+    cnt = rhi[link] - rlo[link] + 1;
+    return cnt <= C;
+}
+__global__ void k_cluster_count(int n, int C, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rlo,
+                                const int* __restrict__ rhi, int* __restrict__ counts) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    const bool live = i == 0 || rhi[i] - rlo[i] + 1 > kLeafMax;
-    int c = 0;
-    if (live) {
-        const int l0 = __float_as_int(nodes[i].q3.x), l1 = __float_as_int(nodes[i].q3.y);
-        c = (l0 < 0 && ((~l0) & kLeafMask) > 0) + (l1 < 0 && ((~l1) & kLeafMask) > 0);
-    }
+    const bool live = i == 0 || rhi[i] - rlo[i] + 1 > C;
+    int c = 0, f, k;
+    if (live) c = (int)cluster_child(left[i], C, rlo, rhi, f, k) + (int)cluster_child(right[i], C, rlo, rhi, f, k);
     counts[i] = c;
 }
-
-__global__ void k_leaf_fill(int n, const int* __restrict__ counts, const int* __restrict__ offsets, const BvhNode* __restrict__ nodes,
-                            float4* __restrict__ leafLo, float4* __restrict__ leafHi) {
+__global__ void k_cluster_fill(int n, int C, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rlo,
+                               const int* __restrict__ rhi, const float4* __restrict__ leafMin, const float4* __restrict__ leafMax,
+                               const float4* __restrict__ nodeMin, const float4* __restrict__ nodeMax, float pad,
+                               const int* __restrict__ counts, const int* __restrict__ offsets, float4* __restrict__ clusterLo,
+                               float4* __restrict__ clusterHi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1 || counts[i] == 0) return;
-    const BvhNode nd = nodes[i];
     int o = offsets[i];
-    const int l0 = __float_as_int(nd.q3.x), l1 = __float_as_int(nd.q3.y);
-    if (l0 < 0 && ((~l0) & kLeafMask) > 0) {
-        leafLo[o] = make_float4(nd.q0.x, nd.q0.y, nd.q0.z, __int_as_float(~l0));
-        leafHi[o] = make_float4(nd.q0.w, nd.q1.x, nd.q1.y, 0.f);
+    const int ch[2] = {left[i], right[i]};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        int first, cnt;
+        if (!cluster_child(ch[c], C, rlo, rhi, first, cnt)) continue;
+        const int L = ch[c];
+        float4 mn = (L < 0) ? leafMin[L & 0x7fffffff] : nodeMin[L], mx = (L < 0) ? leafMax[L & 0x7fffffff] : nodeMax[L];
+        // (the padding of k_emit: the same boxes as in the node array)
+        mn.x -= pad; mn.y -= pad; mn.z -= pad;
+        mx.x += pad; mx.y += pad; mx.z += pad;
+        clusterLo[o] = make_float4(mn.x, mn.y, mn.z, __int_as_float(first));
+        clusterHi[o] = make_float4(mx.x, mx.y, mx.z, __int_as_float(cnt));
         o++;
-    }
-    if (l1 < 0 && ((~l1) & kLeafMask) > 0) {
-        leafLo[o] = make_float4(nd.q1.z, nd.q1.w, nd.q2.x, __int_as_float(~l1));
-        leafHi[o] = make_float4(nd.q2.y, nd.q2.z, nd.q2.w, 0.f);
     }
 }
 
@@ -235,19 +249,25 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
         k_karras<<<G, B, 0, st>>>(keys2, n, left, right, rlo, rhi, parentI, parentL);
         k_refit<<<G, B, 0, st>>>(d_verts, vals2, n, left, right, parentI, parentL, leafMin, leafMax, nodeMin, nodeMax, arrive);
         k_emit<<<G, B, 0, st>>>(n, left, right, rlo, rhi, leafMin, leafMax, nodeMin, nodeMax, pad, sc.nodes);
-        // flat leaf table for the binned visibility kernel (arrive / parentI are free again: counts / offsets)
+        // flat cluster table for the binned visibility kernel (arrive / parentI are free again: counts / offsets); clusters grow
+        // until a camera pose can sort all of them (kMaxBinLeaves), up to kMaxClusterTris triangles each
         int *counts = arrive, *offsets = parentI;
-        k_leaf_count<<<G, B, 0, st>>>(n, rlo, rhi, sc.nodes, counts);
-        IPP_CUDA_CHECK(cudaMemsetAsync(counts + (n - 1), 0, sizeof(int), st));
         size_t scanBytes = scan_tmp_bytes(n);
         void* scanTmp = nullptr;
         IPP_CUDA_CHECK(cudaMalloc(&scanTmp, scanBytes));
-        exclusive_scan_i32(counts, offsets, n, scanTmp, scanBytes, st);
-        IPP_CUDA_CHECK(cudaMemcpyAsync(&sc.nLeaves, offsets + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-        IPP_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int C = kLeafMax;; C *= 2) {
+            k_cluster_count<<<G, B, 0, st>>>(n, C, left, right, rlo, rhi, counts);
+            IPP_CUDA_CHECK(cudaMemsetAsync(counts + (n - 1), 0, sizeof(int), st));
+            exclusive_scan_i32(counts, offsets, n, scanTmp, scanBytes, st);
+            IPP_CUDA_CHECK(cudaMemcpyAsync(&sc.nLeaves, offsets + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+            IPP_CUDA_CHECK(cudaStreamSynchronize(st));
+            sc.leafCap = C;
+            if (sc.nLeaves <= kMaxBinLeaves || C * 2 > kMaxClusterTris) break;
+        }
         sc.leafLo = dalloc<float4>(sc.nLeaves);
         sc.leafHi = dalloc<float4>(sc.nLeaves);
-        k_leaf_fill<<<G, B, 0, st>>>(n, counts, offsets, sc.nodes, sc.leafLo, sc.leafHi);
+        k_cluster_fill<<<G, B, 0, st>>>(n, sc.leafCap, left, right, rlo, rhi, leafMin, leafMax, nodeMin, nodeMax, pad, counts, offsets, sc.leafLo,
+                                        sc.leafHi);
         IPP_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaFree(scanTmp);
     } else {
@@ -263,11 +283,13 @@ void build_bvh(const float* d_verts, const float* d_canon, const float* d_centro
         nd.q3 = make_float4(f0, f1, 0.f, 0.f);
         IPP_CUDA_CHECK(cudaMemcpyAsync(sc.nodes, &nd, sizeof(nd), cudaMemcpyHostToDevice, st));
         sc.nLeaves = 1;
+        sc.leafCap = kLeafMax;
         sc.leafLo = dalloc<float4>(1);
         sc.leafHi = dalloc<float4>(1);
         float4 lo4 = make_float4(nd.q0.x, nd.q0.y, nd.q0.z, 0.f), hi4 = make_float4(nd.q0.w, nd.q1.x, nd.q1.y, 0.f);
-        int ref = (0 << kLeafShift) | 1;
-        memcpy(&lo4.w, &ref, 4);
+        const int first = 0, cnt = 1;
+        memcpy(&lo4.w, &first, 4);
+        memcpy(&hi4.w, &cnt, 4);
         IPP_CUDA_CHECK(cudaMemcpyAsync(sc.leafLo, &lo4, sizeof(lo4), cudaMemcpyHostToDevice, st));
         IPP_CUDA_CHECK(cudaMemcpyAsync(sc.leafHi, &hi4, sizeof(hi4), cudaMemcpyHostToDevice, st));
     }

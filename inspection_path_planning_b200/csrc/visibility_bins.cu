@@ -7,18 +7,19 @@
 //                 sorted by depth (cub::BlockRadixSort, stable, so the order is deterministic).  The CTA also ORs the rectangles
 //                 into a 32x32 tile occupancy mask and an 8x8 supertile mask: empty tiles are never scheduled.
 //   k_visibility_bins  persistent grid, one warp per occupied 128x128 supertile: one coalesced pass over the pose's table keeps the
-//                 entries that touch the supertile (per-warp list in an L2-resident scratch); the tile-independent half of the
-//                 triangle set-up then runs once per triangle of that list into 64-byte records (a second per-warp scratch) with
-//                 a 4-byte header each (depth key of the leaf, tiles of the supertile the triangle's screen box touches), and
-//                 the warp rasterises its <= 16 tiles one after the other: a tile scans the headers front to back, stages the
-//                 records that can touch it, and stops at the first header behind its farthest hit (a list with more triangles
-//                 than the record scratch holds keeps the older scheme: walk the leaves, set their triangles up per tile) --
-//                 strict front-to-back order makes
-//                 the hierarchical depth culling of raster.cuh bite much earlier than the approximate order of a BVH walk, and
-//                 there is no dependent node fetch left on the critical path.
+//                 entries that touch the supertile (per-warp list in a scratch).  The tile-independent half of the triangle set-up
+//                 then runs once per triangle of that list: triangles that can produce a fragment in the supertile become 64-byte
+//                 records (a second per-warp scratch) and, for every tile of the supertile that the triangle's screen box touches,
+//                 one 4-byte entry [depth key of its cluster | record] in that tile's list (a third).  The warp then rasterises its
+//                 <= 16 tiles one after the other: a tile reads its own list front to back, 32 records per staging round, and
+//                 stops at the first entry behind its farthest hit -- strict front-to-back order makes the hierarchical depth
+//                 culling of raster.cuh bite much earlier than the approximate order of a BVH walk, no dependent node fetch is
+//                 left on the critical path, and a tile never looks at a triangle that cannot touch it.  A supertile with more
+//                 surviving triangles than the record scratch holds is split into halves (down to single tiles, which take their
+//                 triangles in several batches).
 //
-// Used when the mesh has <= kMaxLeaves leaves and the image is <= 1024 pixels a side (every asset of the reference); larger
-// inputs take the BVH-walking kernel of visibility.cu.
+// Used when the mesh has <= kMaxBinLeaves clusters of <= kMaxClusterTris triangles (meshes up to ~2 M triangles) and the image is
+// <= 1024 pixels a side; other inputs take the BVH-walking kernel of visibility.cu.
 #include <cub/block/block_radix_sort.cuh>
 
 #include "raster.cuh"
@@ -33,24 +34,29 @@ constexpr int kBinWarps = 4;
 constexpr int kBinThreads = kBinWarps * 32;
 constexpr unsigned long long kNoEntry = ~0ull;
 constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
+constexpr int kBinRecords = 4096;   // set-up triangles (64 B each) a warp can keep for one supertile (or part of one)
 #ifndef IPP_STAGE_MIN
 #define IPP_STAGE_MIN 8
 #endif
 constexpr int kStageMin = IPP_STAGE_MIN;  // waiting records that make a staging round worth running at the end of a header chunk
-constexpr int kBinRecords = 4096;   // set-up triangles (64 B each) a warp can keep for one supertile
 #ifndef IPP_FILTER_UNROLL
 #define IPP_FILTER_UNROLL 4
 #endif
-constexpr int kFilterUnroll = IPP_FILTER_UNROLL;    // table loads a lane keeps in flight while a supertile's list is filtered
+constexpr int kFilterUnroll = IPP_FILTER_UNROLL;
+#ifndef IPP_SUB_ROUND
+#define IPP_SUB_ROUND 16
+#endif
+constexpr int kSubRound = IPP_SUB_ROUND;  // staged triangles rasterised between two refreshes of the tile's depth bounds    // table loads a lane keeps in flight while a supertile's list is filtered
+static_assert(kBinRecords <= 65536, "tile-list entries carry 16 bits of record index");
+static_assert(kMaxClusterTris * 32 <= kBinRecords, "one chunk of 32 list entries must fit the record scratch");
 
 struct __align__(16) BinShared {
     float t[kTilePixels];
     int id[kTilePixels];
     float tri[kPending][kTriWords];
-    uint8_t queue[32 * kLeafMax];  // triangles of one list chunk waiting for set-up: (source lane << 3) | triangle of its leaf
+    uint16_t queue[96];  // records of the tile being rasterised that wait for a staging round
     Snapshot snap;
 };
-static_assert(kLeafMax <= 8, "queue entries hold 3 bits of triangle index");
 
 // ---------------------------------------------------------------------------------------------------------------------
 // leaf table
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
         // depth in 2^-12 steps of the culling range (the low 4 of the 16 key bits stay 0: fewer sort passes)
         // (capped one step below the top: the 12 sorted bits of a real entry never equal those of the empty key)
         const unsigned zq = min((unsigned)fminf(65534.f, floorf(fmaxf(zmin, 0.f) * qscale)) & 0xfff0u, 0xffe0u);
-        const unsigned ref = (unsigned)__float_as_int(lo4.w) & 0x0fffffffu;
+        const unsigned ref = (unsigned)leaf;  // cluster index (first triangle and count: leafLo.w, leafHi.w)
         stage[leaf] = ((unsigned long long)zq << 48) | ((unsigned long long)tx0 << 43) | ((unsigned long long)tx1 << 38) |
                    ((unsigned long long)ty0 << 33) | ((unsigned long long)ty1 << 28) | ref;
         const unsigned bits = ((2u << tx1) - 1u) & ~((1u << tx0) - 1u);
@@ -202,9 +208,13 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
 // ---------------------------------------------------------------------------------------------------------------------
 // K4b
 // ---------------------------------------------------------------------------------------------------------------------
-#ifdef IPP_VIS_DIAG
-__device__ unsigned long long g_diag[1];  // diagnostic build: triangles staged in tiles that stayed open
-#endif
+// A region of a supertile: tile columns x0..x1 and rows y0..y1 (0..3), packed into 8 bits.
+__device__ __forceinline__ unsigned region_pack(unsigned x0, unsigned x1, unsigned y0, unsigned y1) { return x0 | (x1 << 2) | (y0 << 4) | (y1 << 6); }
+__device__ __forceinline__ unsigned region_mask(unsigned r) {  // bit ty * 4 + tx of every tile of the region
+    const unsigned x0 = r & 3u, x1 = (r >> 2) & 3u, y0 = (r >> 4) & 3u, y1 = (r >> 6) & 3u;
+    return (((2u << x1) - (1u << x0)) * 0x1111u) & ((16u << (4 * y1)) - 1u) & ~((1u << (4 * y0)) - 1u);
+}
+
 __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
                                                                  const int* __restrict__ superOffset, int nSnaps,
                                                                  const unsigned long long* __restrict__ table, int stride,
@@ -218,14 +228,11 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of re-read (S2R) inside the loops
     BinShared& S = s_all[warp];
     unsigned long long* list = scratch + (size_t)(blockIdx.x * kBinWarps + warp) * stride;
-    float4* rec = recordsAll + (size_t)(blockIdx.x * kBinWarps + warp) * ((kBinRecords + 32) * 17 / 4);
-    unsigned* hdr = reinterpret_cast<unsigned*>(rec + (size_t)(kBinRecords + 32) * 4);  // one word per record: leaf depth key:16 | tiles:16
-    uint16_t* q16 = reinterpret_cast<uint16_t*>(S.queue);                                // phase 2: records waiting for a staging round
+    float4* rec = recordsAll + (size_t)(blockIdx.x * kBinWarps + warp) * (kBinRecords * 17 / 4);
+    unsigned* hdr = reinterpret_cast<unsigned*>(rec + (size_t)kBinRecords * 4);  // one word per record: cluster depth key:16 | tiles:16
+    uint16_t* q16 = S.queue;
     unsigned long long myRays = 0, myEntries = 0;
-    unsigned myTris = 0, myTiles = 0, mySuperRec = 0, mySuperWalk = 0;  // statistics (lane 0 only matters)
-#ifdef IPP_VIS_DIAG
-    unsigned myLive = 0, myOpen = 0, myOpenTris = 0;
-#endif
+    unsigned myTris = 0, myTiles = 0, mySuperRec = 0, mySuperSplit = 0;  // statistics (lane 0 only matters)
     const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
     const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
     const float zNear = cam.zNear, zFar = cam.zFar;
@@ -255,6 +262,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
             sbit = __ffsll((long long)m) - 1;
         }
         const unsigned ssx = sbit & 7, ssy = sbit >> 3;
+        const uint32_t* poseMask = tileMask + (size_t)si * 32;
 
         // ---- phase 1: the table entries that touch this supertile, still front to back ----
         const int nEnt = __ldg(tableCount + si);
@@ -282,230 +290,230 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         myEntries += (unsigned long long)nEnt;
         __syncwarp();
 
-        // ---- phase 1.5: the pose half of the set-up, once per triangle of the list instead of once per tile that stages it ----
-        // (a leaf rectangle covers most of the 16 tiles, so a triangle was set up by ~10 of them).  The 64-byte records and their
-        // 4-byte headers go to this warp's part of `recordsAll` (L2-resident) in list order; a list with more than kBinRecords
-        // triangles keeps the leaf walk with its per-tile set-up.
-        bool cached;
-        int nRec = 0;
-        {
-            for (int i = lane; i < L; i += 32) nRec += (int)((unsigned)list[i] & kLeafMask);
-#pragma unroll
-            for (int d = 16; d; d >>= 1) nRec += __shfl_xor_sync(0xffffffffu, nRec, d);
-            cached = nRec <= kBinRecords;
-        }
-        if (cached) mySuperRec++;
-        else mySuperWalk++;
-        if (cached) {
-            TileGeom none = {};
-            SuperGeom sgm;
-            sgm.X0 = __fmaf_rn((float)((int)ssx * 4 * kTile), kx, cx);
-            sgm.Y0 = __fmaf_rn((float)((int)ssy * 4 * kTile), ky, cy);
-            sgm.ipx = 1.f / kx;
-            sgm.ipy = 1.f / ky;
-            const float zFarCull = zFar * kDepthTie;
-            int recBase = 0;
-            for (int base = 0; base < L; base += 32) {
-                const int i = base + lane;
-                const unsigned long long e = i < L ? list[i] : 0ull;
-                const int first = (int)(((unsigned)e & 0x0fffffffu) >> kLeafShift);
-                const int cnt = i < L ? (int)((unsigned)e & kLeafMask) : 0;
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                __syncwarp();
-                for (int q = 0; q < cnt; ++q) S.queue[incl - cnt + q] = (uint8_t)((lane << 3) | q);
-                __syncwarp();
-                myTris += total;
-                for (int p0 = 0; p0 < total; p0 += 32) {
-                    const int p = p0 + lane;
-                    const unsigned b = p < total ? S.queue[p] : 0u;
-                    const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
-                    const unsigned zq = __shfl_sync(0xffffffffu, (unsigned)(e >> 48), b >> 3);
-                    unsigned tiles = 0u;  // a rejected triangle is never staged
-                    if (p < total) {
-                        setup_triangle_t<true>(sc, &S.snap, tri, S.tri[lane], ox, oy, oz, zNear, zFarCull, none, &sgm, &tiles);
-                        hdr[recBase + p] = (zq << 16) | tiles;
-                    }
-                    __syncwarp();
-                    // 32 rows of 64 B in shared memory -> 2 KB of records, coalesced (rows past `total` are never read)
-                    const float4* src = reinterpret_cast<const float4*>(&S.tri[0][0]);
-                    float4* dst = rec + (size_t)(recBase + p0) * 4;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) dst[k * 32 + lane] = src[k * 32 + lane];
-                    __syncwarp();
-                }
-                recBase += total;
-            }
-        }
-        __syncwarp();
+        SuperGeom sgm;
+        sgm.X0 = __fmaf_rn((float)((int)ssx * 4 * kTile), kx, cx);
+        sgm.Y0 = __fmaf_rn((float)((int)ssy * 4 * kTile), ky, cy);
+        sgm.ipx = 1.f / kx;
+        sgm.ipy = 1.f / ky;
+        const float zFarCull = zFar * kDepthTie;
 
-        // ---- phase 2: the occupied tiles of the supertile ----
-        for (int tl = 0; tl < 16; ++tl) {
-            const int tx = (int)ssx * 4 + (tl & 3), ty = (int)ssy * 4 + (tl >> 2);
-            const int tpx0 = tx * kTile, tpy0 = ty * kTile;
-            if (tpx0 >= cam.W || tpy0 >= cam.H) continue;
-            const bool occupied = (__ldg(tileMask + (size_t)si * 32 + ty) >> tx) & 1u;
-            if (!occupied && !idImage) continue;
-            const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
-            float zcull = zFar * kDepthTie;  // nothing beyond this depth can matter to any ray of the tile
-            // lane b keeps the depth beyond which nothing can matter to any ray of 8x4 block b (0: block outside the image)
-            float bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zcull : 0.f;
-            TileGeom tg;
-            tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
+        // ---- regions of the supertile: the whole of it, or, when its triangles do not fit the record scratch, halves of it ----
+        unsigned long long stack = (unsigned long long)region_pack(0, 3, 0, 3);
+        int depth = 1;
+        mySuperRec++;
+        while (depth > 0) {
+            const unsigned region = (unsigned)(stack & 0xffull);
+            stack >>= 8;
+            depth--;
+            const unsigned rx0 = region & 3u, rx1 = (region >> 2) & 3u, ry0 = (region >> 4) & 3u, ry1 = (region >> 6) & 3u;
+            const unsigned rmask = region_mask(region);
+            const bool single = rx0 == rx1 && ry0 == ry1;
+            const int atx0 = (int)ssx * 4 + (int)rx0, atx1 = (int)ssx * 4 + (int)rx1, aty0 = (int)ssy * 4 + (int)ry0, aty1 = (int)ssy * 4 + (int)ry1;
+            // a region without an occupied tile has nothing to do (the test hook visits every tile)
+            if (!idImage) {
+                bool any = false;
+                for (int ty = aty0; ty <= aty1; ++ty) any = any || ((__ldg(poseMask + ty) >> atx0) & ((2u << (atx1 - atx0)) - 1u)) != 0u;
+                if (!any) continue;
+            }
+
+            // what a single-tile region keeps across its batches: the tile's farthest hit and whether its hit buffers are in use
+            // (everything else about a tile is rebuilt when its rasterisation starts or resumes: registers are scarce in phase 1.5)
+            float zcullKeep = zFarCull;
             bool inited = false, tileHit = false;
-#ifdef IPP_VIS_DIAG
-            const unsigned trisBefore = myTris;
-#endif
-            // Triangles wait in lane order: lanes < pend carry one each (myTri, its leaf's depth myZ) from the previous chunk.
-            int pend = 0, myTri = 0;
-            float myZ = 0.f;
-            // ---- flush: set up to 32 triangles up in parallel, one per lane, then test them one after the other ----
-            auto flush = [&](bool mineValid) {
-                __syncwarp();
-                bool mineOk = false;
-                if (mineValid) {
-                    if (cached) mineOk = stage_record(rec + (size_t)myTri * 4, S.tri[lane], zcull, tg);
-                    else mineOk = setup_triangle(sc, &S.snap, myTri, S.tri[lane], ox, oy, oz, zNear, zcull, tg);
-                }
-                const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
-#ifdef IPP_VIS_DIAG
-                myLive += __popc(live);
-#endif
-                if (live) {
-                    if (!inited) {
-                        tile_init(S.t, S.id, lane, vw, vh, zFar);
-                        inited = true;
-                    }
-                    __syncwarp();
-                    const bool dirty = raster_staged(live, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
-                    if (__any_sync(0xffffffffu, dirty)) {
-                        tileHit = true;
-                        __syncwarp();
-                        refresh_depth_bounds(S.t, lane, bzReg, zcull);
-                    }
-                }
-            };
-            if (cached) {
-                // the record headers, front to back: a lane keeps the records whose triangle can touch this tile; 32 of them make a
-                // staging round
-                int nq = 0;
-                for (int base = 0; occupied && base < nRec; base += 32) {
-                    const float bound = zcull * 1.000001f + 1e-4f;
+
+            int resumeBase = 0, resumeP0 = 0;
+            bool overflow = false;
+            do {  // batches (only a single-tile region runs more than one)
+                __syncwarp();  // the records and tile lists of the previous batch / region have been read by every lane
+                // ---- phase 1.5: the pose half of the set-up, once per triangle of the list instead of once per tile that stages it.
+                // A triangle that can produce a fragment in the region becomes a 64-byte record with a 4-byte header (depth key of its
+                // cluster, tiles of the supertile its screen box touches); the others are dropped here, so that the tiles scan
+                // fewer headers.
+                int nRecs = 0;
+                bool stop = false;
+                for (int base = resumeBase; base < L && !stop; base += 32) {
                     const int i = base + lane;
-                    const unsigned h = i < nRec ? hdr[i] : 0xffff0000u;
-                    const float zl = (float)(h >> 16) * iq;
-                    // sorted by leaf depth: when the first record of the chunk is behind the farthest hit, so is everything after it
-                    if (__shfl_sync(0xffffffffu, zl, 0) > bound) break;
-                    myEntries += 16ull;  // 32 headers of 4 bytes
-                    const bool hit = i < nRec && ((h >> tl) & 1u) != 0u && zl <= bound;
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (m == 0u) continue;
-                    myTris += __popc(m);
-                    if (hit) q16[nq + __popc(m & ltMask)] = (uint16_t)i;
-                    nq += __popc(m);
-                    __syncwarp();
-                    if (nq >= 32) {
-                        myTri = q16[lane];
-                        const uint16_t moved = q16[32 + lane];
-                        __syncwarp();
-                        q16[lane] = moved;
-                        nq -= 32;
-                        flush(true);
-                    } else if (nq >= kStageMin) {  // a short round now keeps the depth bound, and with it the early exit, fresh
-                        myTri = q16[lane];
-                        const bool mine = lane < nq;
-                        nq = 0;
-                        flush(mine);
+                    const unsigned long long e = i < L ? list[i] : 0ull;
+                    const unsigned r = (unsigned)(e >> 28);
+                    const int tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
+                    const bool inRegion = i < L && tx0 <= atx1 && tx1 >= atx0 && ty0 <= aty1 && ty1 >= aty0;
+                    const unsigned ref = (unsigned)e & 0x0fffffffu;
+                    const int first = inRegion ? __float_as_int(__ldg(&sc.leafLo[ref].w)) : 0;
+                    const int cnt = inRegion ? __float_as_int(__ldg(&sc.leafHi[ref].w)) : 0;
+                    const unsigned zq = (unsigned)(e >> 48);
+                    if (single && base > resumeBase) {
+                        // front to back: nothing behind the tile's farthest hit can matter any more
+                        const float zl0 = (float)__shfl_sync(0xffffffffu, zq, 0) * iq;
+                        if (inited && zl0 > zcullKeep * 1.000001f + 1e-4f) { resumeBase = L; resumeP0 = 0; break; }
                     }
-                }
-                if (nq > 0) {
-                    myTri = q16[lane];
-                    flush(lane < nq);
-                }
-            } else {
-            for (int base = 0; occupied && base < L; base += 32) {
-                float bound = zcull * 1.000001f + 1e-4f;
-                const int i = base + lane;
-                const unsigned long long e = i < L ? list[i] : kNoEntry;
-                const float zl = (float)(unsigned)(e >> 48) * iq;
-                // sorted by depth: when the first entry of the chunk is behind the farthest hit, so is everything after it
-                if (__shfl_sync(0xffffffffu, zl, 0) > bound) break;
-                myEntries += 32ull;
-                const unsigned r = (unsigned)(e >> 28);
-                const int tx0 = (r >> 15) & 31u, tx1 = (r >> 10) & 31u, ty0 = (r >> 5) & 31u, ty1 = r & 31u;
-                const bool hit = i < L && tx0 <= tx && tx <= tx1 && ty0 <= ty && ty <= ty1 && zl <= bound;
-                if (!__any_sync(0xffffffffu, hit)) continue;
-                // the triangles of the leaves that contain the tile, in list order: leaf k contributes positions [P_k, P_k + cnt_k)
-                const int first = (int)(((unsigned)e & 0x0fffffffu) >> kLeafShift);
-                const int cnt = hit ? (int)((unsigned)e & kLeafMask) : 0;
-                int incl = cnt;
+                    int incl = cnt;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    const int excl = incl - cnt;
+                    for (int p0 = (base == resumeBase ? resumeP0 : 0); p0 < total; p0 += 32) {
+                        if (nRecs + 32 > kBinRecords) {  // the scratch is full: this batch ends here
+                            stop = true;
+                            resumeBase = base;
+                            resumeP0 = p0;
+                            break;
+                        }
+                        const int p = p0 + lane;
+                        // the list entry that holds position p: the number of entries whose inclusive prefix is <= p
+                        int src = 0;
+#pragma unroll
+                        for (int sft = 16; sft; sft >>= 1) {
+                            const int v = __shfl_sync(0xffffffffu, incl, min(src + sft - 1, 31));
+                            if (v <= p) src += sft;
+                        }
+                        src = min(src, 31);
+                        const int tri = __shfl_sync(0xffffffffu, first, src) + (p - __shfl_sync(0xffffffffu, excl, src));
+                        const unsigned zqe = __shfl_sync(0xffffffffu, zq, src);
+                        unsigned tiles = 0u;
+                        bool keep = false;
+                        if (p < total) {
+                            keep = setup_triangle_t<true>(sc, &S.snap, tri, S.tri[lane], ox, oy, oz, zNear, zFarCull, TileGeom(), &sgm, &tiles);
+                            tiles &= rmask;
+                            keep = keep && tiles != 0u;
+                        }
+                        myTris += (unsigned)min(32, total - p0);
+                        const unsigned km = __ballot_sync(0xffffffffu, keep);
+                        if (km == 0u) continue;
+                        const int pos = nRecs + __popc(km & ltMask);
+                        if (keep) {
+                            const float4* srcRow = reinterpret_cast<const float4*>(S.tri[lane]);
+                            float4* dst = rec + (size_t)pos * 4;
+                            dst[0] = srcRow[0]; dst[1] = srcRow[1]; dst[2] = srcRow[2]; dst[3] = srcRow[3];
+                        }
+                        if (keep) hdr[pos] = (zqe << 16) | tiles;
+                        nRecs += __popc(km);
+                    }
+                    if (!stop && base + 32 >= L) { resumeBase = L; resumeP0 = 0; }
                 }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (L == 0 || resumeBase >= L) stop = false;
+                overflow = stop;
+                if (overflow && !single) break;  // the region is split instead
                 __syncwarp();
-                for (int q = 0; q < cnt; ++q) S.queue[incl - cnt + q] = (uint8_t)((lane << 3) | q);  // (source lane, triangle of its leaf)
-                __syncwarp();
-                const int pend0 = pend, avail = pend0 + total;
-                myTris += total;
-                // position p of the waiting line: p < pend is lane p's carried triangle, otherwise queue[p - pend]
-                int p = lane;
-                for (; p - lane + 32 <= avail; p += 32) {
-                    const int qp = p - pend0;
-                    const unsigned b = qp >= 0 ? S.queue[qp] : 0u;
-                    const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
-                    const float z = __shfl_sync(0xffffffffu, zl, b >> 3);
-                    if (qp >= 0) { myTri = tri; myZ = z; }
-                    flush(myZ <= bound);  // a flush may have pulled the farthest hit in front of this leaf since it was queued
-                    bound = zcull * 1.000001f + 1e-4f;
+
+                // ---- phase 2: the occupied tiles of the region ----
+                for (int tl = 0; tl < 16; ++tl) {
+                    if (!((rmask >> tl) & 1u)) continue;
+                    const int tx = (int)ssx * 4 + (tl & 3), ty = (int)ssy * 4 + (tl >> 2);
+                    if (tx * kTile >= cam.W || ty * kTile >= cam.H) continue;
+                    const bool occupied = (__ldg(poseMask + ty) >> tx) & 1u;
+                    if (!occupied && !idImage) continue;
+                    const int tpx0 = tx * kTile, tpy0 = ty * kTile;
+                    const int vw = min(kTile, cam.W - tpx0), vh = min(kTile, cam.H - tpy0);  // valid pixels of a border tile
+                    if (nRecs == 0 && !idImage && !(single && inited)) {  // nothing of the region's triangles can touch any tile
+                        myRays += (unsigned long long)(vw * vh);
+                        myTiles++;
+                        continue;
+                    }
+                    TileGeom tg;
+                    tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
+                    // zcull: nothing beyond this depth can matter to any ray of the tile; lane b keeps the same for 8x4 block b in bzReg
+                    // (0: block outside the image)
+                    float zcull = zFarCull, bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zFarCull : 0.f;
+                    if (single && inited) refresh_depth_bounds(S.t, lane, bzReg, zcull);  // a later batch of the same tile
+                    else { inited = false; tileHit = false; }
+                    // ---- flush: stage up to 32 records in parallel, one per lane, then test them kSubRound at a time ----
+                    auto flush = [&](bool mineValid, int myRec) {
+                        __syncwarp();
+                        bool mineOk = false;
+                        if (mineValid) mineOk = stage_record(rec + (size_t)myRec * 4, S.tri[lane], zcull, tg);
+                        const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
+                        if (live) {
+                            if (!inited) {
+                                tile_init(S.t, S.id, lane, vw, vh, zFar);
+                                inited = true;
+                            }
+                            __syncwarp();
+                            // kSubRound triangles at a time: the farthest hits of the tile and of its 8x4 blocks are refreshed in
+                            // between, so that what the front-most triangles of the round cover already culls the ones behind them
+#pragma unroll 1
+                            for (int s0 = 0; s0 < 32; s0 += kSubRound) {
+                                const unsigned sub = live & (kSubRound >= 32 ? 0xffffffffu : (((1u << (kSubRound & 31)) - 1u) << s0));
+                                if (sub == 0u) continue;
+                                const bool dirty = raster_staged(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
+                                if (__any_sync(0xffffffffu, dirty)) {
+                                    tileHit = true;
+                                    __syncwarp();
+                                    refresh_depth_bounds(S.t, lane, bzReg, zcull);
+                                }
+                            }
+                        }
+                    };
+                    // the record headers, front to back: a lane keeps the records whose triangle can touch this tile; 32 of them make a
+                    // staging round (the next chunk of headers is requested before the current one is worked on)
+                    int nq = 0;
+                    unsigned hNext = (occupied && lane < nRecs) ? hdr[lane] : 0xffff0000u;
+                    for (int base = 0; occupied && base < nRecs; base += 32) {
+                        const float bound = zcull * 1.000001f + 1e-4f;
+                        const int i = base + lane;
+                        const unsigned h = hNext;
+                        hNext = (i + 32 < nRecs) ? hdr[i + 32] : 0xffff0000u;
+                        const float zl = (float)(h >> 16) * iq;
+                        // sorted by cluster depth: when the first record of the chunk is behind the farthest hit, so is everything after it
+                        if (__shfl_sync(0xffffffffu, zl, 0) > bound) break;
+                        myEntries += 16ull;  // 32 headers of 4 bytes
+                        const bool hit = i < nRecs && ((h >> tl) & 1u) != 0u && zl <= bound;
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (m == 0u) continue;
+                        myTris += __popc(m);
+                        if (hit) q16[nq + __popc(m & ltMask)] = (uint16_t)i;
+                        nq += __popc(m);
+                        __syncwarp();
+                        if (nq >= 32) {
+                            const int myRec = q16[lane];
+                            const uint16_t moved = q16[32 + lane];
+                            __syncwarp();
+                            q16[lane] = moved;
+                            nq -= 32;
+                            flush(true, myRec);
+                        } else if (nq >= kStageMin) {  // a short round now keeps the depth bound, and with it the early exit, fresh
+                            const int myRec = q16[lane];
+                            const bool mine = lane < nq;
+                            nq = 0;
+                            flush(mine, myRec);
+                        }
+                    }
+                    if (nq > 0) flush(lane < nq, q16[lane]);
+                    __syncwarp();
+                    zcullKeep = zcull;
+                    if (single && overflow) continue;  // more batches of this tile's triangles follow
+                    // ---- the winners ----
+                    if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
+                    __syncwarp();
+                    if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
+                    myRays += (unsigned long long)(vw * vh);
+                    myTiles++;
+                    __syncwarp();
                 }
-                {   // what is left waits in lanes 0 .. avail - (p - lane) - 1
-                    const int qp = p - pend0;
-                    const bool take = p < avail && qp >= 0;
-                    const unsigned b = take ? S.queue[qp] : 0u;
-                    const int tri = __shfl_sync(0xffffffffu, first, b >> 3) + (int)(b & 7u);
-                    const float z = __shfl_sync(0xffffffffu, zl, b >> 3);
-                    if (take) { myTri = tri; myZ = z; }
-                    pend = avail - (p - lane);
+            } while (single && overflow);
+            if (overflow && !single) {
+                // halves, the longer side first
+                mySuperSplit++;
+                if (rx1 - rx0 >= ry1 - ry0) {
+                    const unsigned xm = (rx0 + rx1) >> 1;
+                    stack = (stack << 16) | ((unsigned long long)region_pack(xm + 1, rx1, ry0, ry1) << 8) | region_pack(rx0, xm, ry0, ry1);
+                } else {
+                    const unsigned ym = (ry0 + ry1) >> 1;
+                    stack = (stack << 16) | ((unsigned long long)region_pack(rx0, rx1, ym + 1, ry1) << 8) | region_pack(rx0, rx1, ry0, ym);
                 }
+                depth += 2;
             }
-            if (pend > 0) flush(lane < pend && myZ <= zcull * 1.000001f + 1e-4f);
-            }
-            __syncwarp();
-            // ---- the winners ----
-            if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
-            __syncwarp();
-            if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
-            myRays += (unsigned long long)(vw * vh);
-            myTiles++;
-#ifdef IPP_VIS_DIAG
-            if (zcull == zFar * kDepthTie) {  // some ray of the tile never hit: the list was walked to its end
-                myOpen++;
-                myOpenTris += myTris - trisBefore;
-            }
-#endif
-            __syncwarp();
         }
     }
-    if (lane == 0 && myTiles) {
+    if (lane == 0 && (myTiles || mySuperRec)) {
         atomicAdd(&counters[0], myRays);
         atomicAdd(&counters[3], (unsigned long long)myTris);
         atomicAdd(&counters[4], (unsigned long long)myTiles);
         atomicAdd(&counters[5], myEntries);
         atomicAdd(&counters[8], (unsigned long long)mySuperRec);
-        atomicAdd(&counters[9], (unsigned long long)mySuperWalk);
-#ifdef IPP_VIS_DIAG
-        atomicAdd(&counters[6], (unsigned long long)myLive);
-        atomicAdd(&counters[7], (unsigned long long)myOpen);
-        atomicAdd(&g_diag[0], (unsigned long long)myOpenTris);
-#endif
+        atomicAdd(&counters[9], (unsigned long long)mySuperSplit);
     }
 }
 
@@ -536,7 +544,7 @@ int bins_grid_blocks() {
     return sms * perSM;
 }
 int bins_warps_per_block() { return kBinWarps; }
-size_t bins_record_floats_per_warp() { return (size_t)(kBinRecords + 32) * 17; }  // 64-byte records + 4-byte headers
+size_t bins_record_floats_per_warp() { return (size_t)kBinRecords * 17; }  // 64-byte records + 4-byte headers
 
 // size classes of the per-pose sort (threads x keys per thread); stride of a pose's table = capacity of its class
 struct SortClass { int capacity; };
@@ -572,12 +580,6 @@ void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, cons
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
     k_visibility_bins<<<grid, kBinThreads, 0, st>>>(sc, cam, d_snaps, d_superOffset, nSnaps, b.table, b.stride, b.tableCount, b.tileMask,
                                                    b.superMask, b.scratch, b.records, d_flags, d_idImage, d_counters);
-#ifdef IPP_VIS_DIAG
-    unsigned long long d[1];
-    cudaStreamSynchronize(st);
-    cudaMemcpyFromSymbol(d, g_diag, sizeof(d));
-    fprintf(stderr, "[vis diag, cumulative] triangles staged in open tiles %llu\n", d[0]);
-#endif
 }
 
 }  // namespace ipp

@@ -264,7 +264,7 @@ def test_full_resolution_config2_edges_of_the_bench_population(oracle_mod):
         g.visibility_stats(reset=True)
         stats, seen = _check_edges_pooled(g, mesh_path("mockup_only"), sp, chosen, g.T)
         vs = g.visibility_stats()
-        assert vs["supertiles_records"] > 0 and vs["supertiles_leaf_walk"] <= 0.02 * vs["supertiles_records"], vs
+        assert vs["supertiles"] > 0 and vs["supertile_splits"] <= 0.02 * vs["supertiles"], vs
         assert stats["seen"] > 20000, stats
         # plan 0: fitness row = area of the union of its edges' seen sets (energy gate off, as in the bench)
         plan0 = [[int(x)] for x in plans[0]]
@@ -300,8 +300,7 @@ def test_full_resolution_luis4_edges_take_the_record_path(oracle_mod):
         g.visibility_stats(reset=True)
         stats, _ = _check_edges_pooled(g, mesh_path("luis4"), sp, edges, g.T)
         vs = g.visibility_stats()
-        assert vs["supertiles_records"] > 0, vs
-        assert vs["supertiles_leaf_walk"] <= 0.02 * vs["supertiles_records"], vs
+        assert vs["supertiles"] > 0 and vs["supertile_splits"] <= 0.02 * vs["supertiles"], vs
         assert stats["seen"] > 5000, stats
     finally:
         g.close()
