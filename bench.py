@@ -378,6 +378,7 @@ def run_c3(args, L, comm, local, peaks):
     cnt = ev.counters()
     cold = {"s": cold_s, "plans_per_s": pop / cold_s, "edges_rendered_all_ranks": int(allsum(cnt["edges_rendered"])),
             "edges_rendered_this_rank": cnt["edges_rendered"], "camera_poses_all_ranks": int(allsum(cnt["snapshots"])),
+            "camera_poses_rendered_all_ranks": int(allsum(cnt["snapshots_rendered"])),
             "rays_per_s": allsum(cnt["rays"]) / cold_s, "memo_rows_per_rank": ev.memo_size(),
             "kernel_ms_this_rank": {"edge_visibility": ev.kernel_time(1)[0], "leaf_tables": ev.kernel_time(5)[0],
                                     "edge_collision": ev.kernel_time(2)[0], "plan_reduce": ev.kernel_time(0)[0]}}
@@ -696,7 +697,10 @@ def run_gpu(args):
         "rays_per_s": rays_total / (ms_total * 1e-3),
         "rays_note": "pixel-centre rays of the 32x32 tiles actually rasterised; tiles the cluster tables prove empty issue none",
         "pixels_resolved_per_s": allsum_snap * SPECS[3] * SPECS[3] / (ms_total * 1e-3),
-        "snapshots_per_step": cnt["snapshots"] / args.steps, "edges_rendered_per_step": cnt["edges_rendered"] / args.steps,
+        "snapshots_per_step": cnt["snapshots"] / args.steps, "snapshots_rendered_per_step": cnt["snapshots_rendered"] / args.steps,
+        "snapshots_note": "camera poses of the edges rendered (what the reference renders) / poses K4 actually rendered: bit-identical poses that "
+                          "several edges of a batch share are rendered once (pose_dedupe.cu)",
+        "edges_rendered_per_step": cnt["edges_rendered"] / args.steps,
         "kernel_ms_per_step": {"edge_visibility": vis_ms / args.steps, "leaf_tables": tab_ms / args.steps, "plan_reduce": red_ms / args.steps,
                                "edge_collision": col_ms / args.steps},
         "clocks": clocks,

@@ -164,8 +164,9 @@ int ipp_flush_l2(ipp_t* h);
  * SMs: a size inside L2 gives the L2 read peak bench.py sets the visibility kernel's lts__t_bytes rate against, a size beyond it
  * the HBM read peak */
 int ipp_read_bandwidth(ipp_t* h, int64_t bytes, int reps, double* gbs);
-/* counters since the last reset: [0] kernel launches, [1] pixel-centre rays issued, [2] snapshots rendered,
- * [3] edges rendered, [4] collision queries, [5] plan_reduce launches, [6] plans reduced, [7] bitmap rows read */
+/* counters since the last reset: [0] kernel launches, [1] pixel-centre rays issued, [2] camera poses of the edges rendered (what
+ * the reference renders: CameraEstimator.cpp:131-178), [3] edges rendered, [4] collision queries, [5] plan_reduce launches,
+ * [6] plans reduced, [7] camera poses actually rendered (poses that several edges of a batch share are rendered once) */
 int ipp_counters(ipp_t* h, int64_t* out8, int reset);
 /* statistics of the edge-visibility kernel since the last reset (reset by ipp_counters too):
  * [0] acceleration-structure data fetched in 64-byte units (BVH nodes of the tile-walking variant, 8 leaf-bin entries of the

@@ -27,6 +27,7 @@ UNITS = [
     ("lbvh.cu", []),
     ("visibility.cu", []),
     ("visibility_bins.cu", []),
+    ("pose_dedupe.cu", []),
     ("comm.cu", []),
     ("ipp_api.cu", []),
     ("mesh_io.cpp", []),

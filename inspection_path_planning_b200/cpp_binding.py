@@ -398,7 +398,7 @@ class PlanCoverageEstimator(object):
     def counters(self, reset=False):
         out = np.zeros(8, dtype=np.int64)
         _lib.check(self._L.ipp_counters(self._h, out.ctypes.data_as(_lib.c_i64p), int(reset)))
-        keys = ["launches", "rays", "snapshots", "edges_rendered", "collision_queries", "reduce_launches", "plans_reduced", "rows_read"]
+        keys = ["launches", "rays", "snapshots", "edges_rendered", "collision_queries", "reduce_launches", "plans_reduced", "snapshots_rendered"]
         return dict(zip(keys, (int(x) for x in out)))
 
     def visibility_stats(self, reset=False):

@@ -68,9 +68,11 @@ struct DeviceScene {
 struct Snapshot {
     double f[3], s[3], u[3];  // look-at basis (world space)
     float eye[3];
-    int slot;                 // flag row within the current batch
+    int slot;                 // as made by K3: flag row (edge) within the current batch; as seen by K4: first entry of this pose's
+    int slotCount;            // flag rows in the batch's slot list, and how many there are (pose_dedupe.cu: edges that share a pose)
     int rx0, ry0, rnx, rny;   // rectangle of 32x32 macro tiles that may see the scene
 };
+static_assert(sizeof(Snapshot) <= 128, "the visibility kernels copy a Snapshot with one 4-byte load per lane");
 
 struct CameraParams {
     double tanX, tanY;

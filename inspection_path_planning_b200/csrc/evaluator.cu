@@ -168,6 +168,7 @@ Evaluator::Evaluator(const std::string& scenePath, const double specs[8], bool p
             maxSnapsPerBatch_ = std::max<int64_t>(64, std::min<int64_t>(maxSnapsPerBatch_, tableBudget / ((int64_t)bins_.stride * 8)));
         }
     }
+    if (const char* e = getenv("IPP_POSE_DEDUPE")) poseDedupe_ = atoi(e) != 0;
     if (const char* e = getenv("IPP_MAX_POSES_PER_BATCH")) maxSnapsPerBatch_ = std::max<int64_t>(1, std::min<int64_t>(maxSnapsPerBatch_, atoll(e)));
     d_countsAll_ = dalloc<int>(nKeys_ + 1);
     d_rows_ = dalloc<uint32_t>((size_t)(rowCapacity_ + 1) * rowWords_);
@@ -214,6 +215,7 @@ Evaluator::~Evaluator() {
     cudaFree(d_scalars_); cudaFreeHost(h_scalars_); cudaFree(d_rows_); cudaFree(d_freeStack_);
     cudaFree(d_flags_); cudaFree(d_rowOfSlot_); cudaFree(d_counts_); cudaFree(d_snapOffset_);
     cudaFree(d_snaps_); cudaFree(d_ntiles_); cudaFree(d_tileOffset_); cudaFree(d_scanTmp_);
+    cudaFree(d_snapsU_); cudaFree(d_ntilesU_); cudaFree(d_slotList_); cudaFree(d_dedupeWork_); cudaFree(d_dedupeIWork_); cudaFree(d_dedupeTmp_);
     cudaFree(d_visCounters_); cudaFree(d_angleOne_);
     cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
     cudaFree(bins_.scratch); cudaFree(bins_.records); cudaFree(d_superOffset_); cudaFree(d_countsAll_);
@@ -295,9 +297,9 @@ void Evaluator::counters(int64_t out[8], bool reset) {
     IPP_CUDA_CHECK(cudaMemcpyAsync(&rays, d_visCounters_, sizeof(rays), cudaMemcpyDeviceToHost, stream_));
     sync();
     out[0] = nLaunches_; out[1] = (int64_t)rays; out[2] = nSnapshots_; out[3] = nEdgesRendered_;
-    out[4] = nCollisionQueries_; out[5] = nReduceLaunches_; out[6] = nPlansReduced_; out[7] = nRowsRead_;
+    out[4] = nCollisionQueries_; out[5] = nReduceLaunches_; out[6] = nPlansReduced_; out[7] = nSnapshotsRendered_;
     if (reset) {
-        nLaunches_ = nSnapshots_ = nEdgesRendered_ = nCollisionQueries_ = nReduceLaunches_ = nPlansReduced_ = nRowsRead_ = 0;
+        nLaunches_ = nSnapshots_ = nEdgesRendered_ = nCollisionQueries_ = nReduceLaunches_ = nPlansReduced_ = nRowsRead_ = nSnapshotsRendered_ = 0;
         IPP_CUDA_CHECK(cudaMemsetAsync(d_visCounters_, 0, 16 * sizeof(unsigned long long), stream_));
     }
 }
@@ -391,6 +393,12 @@ void Evaluator::ensureSnapBuffers(int64_t nSnaps) {
         d_snaps_ = dalloc<Snapshot>(snapCap_);
         d_ntiles_ = dalloc<int>(snapCap_);
         d_tileOffset_ = dalloc<int>(snapCap_);
+        cudaFree(d_snapsU_); cudaFree(d_ntilesU_); cudaFree(d_slotList_); cudaFree(d_dedupeWork_); cudaFree(d_dedupeIWork_);
+        d_snapsU_ = dalloc<Snapshot>(snapCap_);
+        d_ntilesU_ = dalloc<int>(snapCap_);
+        d_slotList_ = dalloc<int>(snapCap_);
+        d_dedupeWork_ = dalloc<unsigned long long>((size_t)snapCap_ * 2);
+        d_dedupeIWork_ = dalloc<int>((size_t)snapCap_ * 7);
         if (useBins_) {
             cudaFree(bins_.table); cudaFree(bins_.tableCount); cudaFree(bins_.tileMask); cudaFree(bins_.superMask); cudaFree(bins_.nSuper);
             cudaFree(d_superOffset_);
@@ -417,11 +425,26 @@ void Evaluator::setUseBins(bool on) {
     snapCap_ = 0;  // buffers are re-made for the variant on the next batch
 }
 
-// K4 for the nSnaps camera poses in d_snaps_ (either variant); d_idImage: test hook
+// K4 for the nSnaps camera poses in d_snaps_ (either variant); d_idImage: test hook.  Poses that several edges of the batch share
+// are rendered once (pose_dedupe.cu): the kernels see the unique poses in d_snapsU_.
 void Evaluator::renderSnapshots(int nSnaps, int32_t* d_idImage) {
+    if (nSnaps <= 0) return;
+    const size_t need = pose_dedupe_tmp_bytes(nSnaps);
+    if (need > dedupeTmpBytes_) {
+        cudaFree(d_dedupeTmp_);
+        dedupeTmpBytes_ = need * 2;
+        IPP_CUDA_CHECK(cudaMalloc(&d_dedupeTmp_, dedupeTmpBytes_));
+    }
+    groupBegin(KG_PLAN);
+    launch_pose_dedupe(d_snaps_, d_ntiles_, nSnaps, poseDedupe_ && nSnaps > 1, d_snapsU_, d_ntilesU_, d_slotList_, d_scalars_ + 5, d_dedupeWork_,
+                       d_dedupeIWork_, d_dedupeTmp_, dedupeTmpBytes_, stream_);
+    groupEnd(KG_PLAN);
+    nLaunches_ += (poseDedupe_ && nSnaps > 1) ? 7 : 1;
+    const int nU = readInt(d_scalars_ + 5);
+    nSnapshotsRendered_ += nU;
     if (useBins_) {
         groupBegin(KG_TABLE);
-        launch_leaf_table(scene_, cam_, d_snaps_, nSnaps, bins_, stream_);
+        launch_leaf_table(scene_, cam_, d_snapsU_, nU, bins_, stream_);
         groupEnd(KG_TABLE);
         if (d_idImage) {
             // test hook: every supertile of the image is scheduled so that background pixels are reported too
@@ -434,19 +457,20 @@ void Evaluator::renderSnapshots(int nSnaps, int32_t* d_idImage) {
             IPP_CUDA_CHECK(cudaMemcpyAsync(bins_.nSuper, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, stream_));
             sync();
         }
-        IPP_CUDA_CHECK(cudaMemsetAsync(bins_.nSuper + nSnaps, 0, sizeof(int), stream_));
-        exclusiveScan(bins_.nSuper, d_superOffset_, nSnaps + 1);
-        int totalSuper = readInt(d_superOffset_ + nSnaps);
+        IPP_CUDA_CHECK(cudaMemsetAsync(bins_.nSuper + nU, 0, sizeof(int), stream_));
+        exclusiveScan(bins_.nSuper, d_superOffset_, nU + 1);
+        int totalSuper = readInt(d_superOffset_ + nU);
         groupBegin(KG_VISIBILITY);
-        launch_visibility_bins(scene_, cam_, d_snaps_, d_superOffset_, nSnaps, totalSuper, bins_, d_flags_, d_idImage, d_visCounters_, stream_);
+        launch_visibility_bins(scene_, cam_, d_snapsU_, d_superOffset_, nU, totalSuper, bins_, d_flags_, d_slotList_, d_idImage, d_visCounters_,
+                               stream_);
         groupEnd(KG_VISIBILITY);
         nLaunches_ += 3;
     } else {
-        IPP_CUDA_CHECK(cudaMemsetAsync(d_ntiles_ + nSnaps, 0, sizeof(int), stream_));
-        exclusiveScan(d_ntiles_, d_tileOffset_, nSnaps + 1);
-        int totalTiles = readInt(d_tileOffset_ + nSnaps);
+        IPP_CUDA_CHECK(cudaMemsetAsync(d_ntilesU_ + nU, 0, sizeof(int), stream_));
+        exclusiveScan(d_ntilesU_, d_tileOffset_, nU + 1);
+        int totalTiles = readInt(d_tileOffset_ + nU);
         groupBegin(KG_VISIBILITY);
-        launch_visibility(scene_, cam_, d_snaps_, d_tileOffset_, nSnaps, totalTiles, d_flags_, d_idImage, d_visCounters_, stream_);
+        launch_visibility(scene_, cam_, d_snapsU_, d_tileOffset_, nU, totalTiles, d_flags_, d_slotList_, d_idImage, d_visCounters_, stream_);
         groupEnd(KG_VISIBILITY);
         nLaunches_ += 2;
     }

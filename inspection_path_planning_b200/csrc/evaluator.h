@@ -149,6 +149,14 @@ class Evaluator {
     uint8_t* d_flags_ = nullptr;
     int *d_rowOfSlot_ = nullptr, *d_counts_ = nullptr, *d_snapOffset_ = nullptr;
     Snapshot* d_snaps_ = nullptr;
+    // unique camera poses of a batch and the edge rows each of them serves (pose_dedupe.cu)
+    Snapshot* d_snapsU_ = nullptr;
+    int *d_ntilesU_ = nullptr, *d_slotList_ = nullptr, *d_dedupeIWork_ = nullptr;
+    unsigned long long* d_dedupeWork_ = nullptr;
+    void* d_dedupeTmp_ = nullptr;
+    size_t dedupeTmpBytes_ = 0;
+    bool poseDedupe_ = true;
+    int64_t nSnapshotsRendered_ = 0;
     int *d_ntiles_ = nullptr, *d_tileOffset_ = nullptr;
     int64_t snapCap_ = 0;
     void* d_scanTmp_ = nullptr;

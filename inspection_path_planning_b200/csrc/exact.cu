@@ -190,6 +190,7 @@ __device__ void make_snapshot(Snapshot& S, const float eye[3], const D3& center,
     S.u[0] = u.x; S.u[1] = u.y; S.u[2] = u.z;
     S.eye[0] = eye[0]; S.eye[1] = eye[1]; S.eye[2] = eye[2];
     S.slot = slot;
+    S.slotCount = 1;
     // conservative screen rectangle of the (slightly padded) scene box
     const int mtx = (cam.W + 31) / 32, mty = (cam.H + 31) / 32;
     double pad = 1e-3;

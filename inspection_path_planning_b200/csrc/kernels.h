@@ -90,7 +90,7 @@ void free_bvh(DeviceScene& sc);
 // Casts one ray through every pixel centre of the macro tiles listed for the snapshots and sets flags[slot * Tpad + id] = 1
 // for the nearest triangle.  d_tileOffset = exclusive scan of tiles per snapshot, totalTiles its sum.
 void launch_visibility(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_tileOffset, int nSnaps,
-                       int64_t totalTiles, uint8_t* d_flags, int32_t* d_idImage /*nullable test hook*/,
+                       int64_t totalTiles, uint8_t* d_flags, const int* d_slotList, int32_t* d_idImage /*nullable test hook*/,
                        unsigned long long* d_rayCounter, cudaStream_t st);
 // flags[slot][Tpad] (bytes) -> bitmap rows; clears the flags
 void launch_pack_rows(uint8_t* d_flags, int nSlots, int Tpad, const int* d_rowOfSlot, uint32_t* d_rows, int64_t rowWords, cudaStream_t st);
@@ -118,8 +118,12 @@ void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Sna
                        cudaStream_t st);
 // d_superOffset = exclusive scan of BinBuffers::nSuper (nSnaps + 1 entries), totalSuper its last entry
 void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_superOffset, int nSnaps,
-                            int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters,
-                            cudaStream_t st);
+                            int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, const int* d_slotList, int32_t* d_idImage,
+                            unsigned long long* d_counters, cudaStream_t st);
+// pose_dedupe.cu -- camera poses several edges of a batch share are rendered once (Snapshot::slot / slotCount -> d_slotList)
+size_t pose_dedupe_tmp_bytes(int n);
+void launch_pose_dedupe(const Snapshot* d_snaps, const int* d_ntiles, int n, bool enabled, Snapshot* d_out, int* d_ntilesOut, int* d_slotList,
+                        int* d_nUniq, unsigned long long* d_work, int* d_iwork, void* d_tmp, size_t tmpBytes, cudaStream_t st);
 size_t sort_tmp_bytes(int n);
 // the same pseudo-random order of a key set on every rank (contiguous chunks of it are random samples of the set)
 void scrambled_order_i32(const int* d_in, int* d_out, int n, void* d_tmp, size_t tmpBytes, cudaStream_t st);

@@ -268,9 +268,9 @@ __device__ __forceinline__ void refresh_depth_bounds(const float* __restrict__ S
     zcull = zm;
 }
 
-// The winners: one byte store per run of equal ids inside an 8x4 block (flags[id] = 1); optional id image for the test hook.
-__device__ __forceinline__ void tile_output(const int* __restrict__ Sid, int lane, uint8_t* __restrict__ flagRow, int32_t* __restrict__ idImage,
-                                            int tpx0, int tpy0, int W, int H) {
+// The winners: one byte store per run of equal ids inside an 8x4 block (flagRow[id] = 1); optional id image for the test hook.
+__device__ __forceinline__ void tile_output_row(const int* __restrict__ Sid, int lane, uint8_t* __restrict__ flagRow, int32_t* __restrict__ idImage,
+                                                int tpx0, int tpy0, int W, int H) {
 #pragma unroll 4
     for (int k = 0; k < kTilePixels / 32; ++k) {
         const int id = Sid[k * 32 + lane];
@@ -282,6 +282,15 @@ __device__ __forceinline__ void tile_output(const int* __restrict__ Sid, int lan
             if (px < W && py < H) idImage[(size_t)py * W + px] = id == kNoId ? -1 : id;
         }
     }
+}
+// ... into the flag row of every edge that shares this camera pose (slots[0 .. nSlots), see pose_dedupe.cu: one row unless several
+// edges meet at the pose)
+__device__ __forceinline__ void tile_output(const int* __restrict__ Sid, int lane, uint8_t* __restrict__ flags, size_t Tpad,
+                                            const int* __restrict__ slots, int nSlots, int32_t* __restrict__ idImage, int tpx0, int tpy0, int W,
+                                            int H) {
+    tile_output_row(Sid, lane, flags + (size_t)__ldg(slots) * Tpad, idImage, tpx0, tpy0, W, H);
+#pragma unroll 1
+    for (int q = 1; q < nSlots; ++q) tile_output_row(Sid, lane, flags + (size_t)__ldg(slots + q) * Tpad, nullptr, tpx0, tpy0, W, H);
 }
 
 // Work-list lookup of the persistent kernels.

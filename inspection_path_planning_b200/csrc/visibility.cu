@@ -116,7 +116,7 @@ struct WarpShared {
 
 __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, CameraParams cam, const Snapshot* __restrict__ snaps,
                                                             const int* __restrict__ tileOffset, int nSnaps, long long totalTiles,
-                                                            uint8_t* __restrict__ flags, int32_t* __restrict__ idImage,
+                                                            uint8_t* __restrict__ flags, const int* __restrict__ slotList, int32_t* __restrict__ idImage,
                                                             unsigned long long* __restrict__ counters) {
     __shared__ WarpShared s_all[kVisWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kVisThreads, 5) k_visibility(DeviceScene sc, C
             }
             __syncwarp();
             // ---- the winners ----
-            if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
+            if (tileHit || idImage) tile_output(S.id, lane, flags, (size_t)sc.Tpad, slotList + S.snap.slot, S.snap.slotCount, idImage, tpx0, tpy0, cam.W, cam.H);
             if (lane == 0) myRays += (unsigned long long)(vw * vh);
             myTiles++;
             __syncwarp();
@@ -373,7 +373,8 @@ int visibility_grid_blocks() {
 }
 
 void launch_visibility(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_tileOffset, int nSnaps,
-                       int64_t totalTiles, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters, cudaStream_t st) {
+                       int64_t totalTiles, uint8_t* d_flags, const int* d_slotList, int32_t* d_idImage, unsigned long long* d_counters,
+                       cudaStream_t st) {
     if (totalTiles <= 0 || nSnaps <= 0) return;
     static int blocks = 0;
     if (!blocks) blocks = visibility_grid_blocks();
@@ -381,7 +382,7 @@ void launch_visibility(const DeviceScene& sc, const CameraParams& cam, const Sna
     int grid = (int)std::min<long long>(blocks, groups);
     // counters[1] is the tile cursor of this launch
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
-    k_visibility<<<grid, kVisThreads, 0, st>>>(sc, cam, d_snaps, d_tileOffset, nSnaps, (long long)totalTiles, d_flags, d_idImage, d_counters);
+    k_visibility<<<grid, kVisThreads, 0, st>>>(sc, cam, d_snaps, d_tileOffset, nSnaps, (long long)totalTiles, d_flags, d_slotList, d_idImage, d_counters);
 }
 
 void launch_pack_rows(uint8_t* d_flags, int nSlots, int Tpad, const int* d_rowOfSlot, uint32_t* d_rows, int64_t rowWords, cudaStream_t st) {

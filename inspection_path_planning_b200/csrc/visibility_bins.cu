@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                                                                  const int* __restrict__ tableCount, const uint32_t* __restrict__ tileMask,
                                                                  const unsigned long long* __restrict__ superMask,
                                                                  unsigned long long* scratch, float4* recordsAll, uint8_t* __restrict__ flags,
-                                                                 int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters) {
+                                                                 const int* __restrict__ slotList, int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters) {
     __shared__ BinShared s_all[kBinWarps];
     const int warp = threadIdx.x >> 5;
     int lane;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                     // ---- the winners ----
                     if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
                     __syncwarp();
-                    if (tileHit || idImage) tile_output(S.id, lane, flags + (size_t)S.snap.slot * sc.Tpad, idImage, tpx0, tpy0, cam.W, cam.H);
+                    if (tileHit || idImage) tile_output(S.id, lane, flags, (size_t)sc.Tpad, slotList + S.snap.slot, S.snap.slotCount, idImage, tpx0, tpy0, cam.W, cam.H);
                     myRays += (unsigned long long)(vw * vh);
                     myTiles++;
                     __syncwarp();
@@ -571,15 +571,15 @@ void launch_leaf_table(const DeviceScene& sc, const CameraParams& cam, const Sna
 }
 
 void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, const Snapshot* d_snaps, const int* d_superOffset, int nSnaps,
-                            int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, int32_t* d_idImage, unsigned long long* d_counters,
-                            cudaStream_t st) {
+                            int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, const int* d_slotList, int32_t* d_idImage,
+                            unsigned long long* d_counters, cudaStream_t st) {
     if (totalSuper <= 0 || nSnaps <= 0) return;
     long long groups = (totalSuper + kBinWarps - 1) / kBinWarps;
     int grid = (int)std::min<long long>(b.gridBlocks, groups);
     // counters[1] is the work cursor of this launch
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
     k_visibility_bins<<<grid, kBinThreads, 0, st>>>(sc, cam, d_snaps, d_superOffset, nSnaps, b.table, b.stride, b.tableCount, b.tileMask,
-                                                   b.superMask, b.scratch, b.records, d_flags, d_idImage, d_counters);
+                                                   b.superMask, b.scratch, b.records, d_flags, d_slotList, d_idImage, d_counters);
 }
 
 }  // namespace ipp
