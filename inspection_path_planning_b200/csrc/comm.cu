@@ -157,6 +157,14 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
     cudaStream_t st = ev.stream();
     const int64_t mine = hi - lo;
     const int64_t g0 = offsets[lo], nGenes = offsets[hi] - g0;
+    // every rank holds the whole population: a bad box id is found by all of them here, before the first collective
+    // (assert at PlanInterpreterBoxOrder.cpp:282)
+    {
+        const int N = ev.numBoxes();
+        const int64_t all = pop > 0 ? offsets[pop] : 0;
+        for (int64_t k = 0; k < all; ++k)
+            if (ids[k] < 0 || ids[k] >= N) throw std::out_of_range("libipp: box id out of range");
+    }
     if (c->world * per * 4 > c->gatherCap) {
         cudaFree(c->d_gather);
         c->gatherCap = c->world * per * 4 + 1024;

@@ -33,7 +33,7 @@ constexpr int kLeafMax = 8;          // triangles per BVH leaf
 constexpr int kLeafShift = 4;        // leaf link: ~link = (first << kLeafShift) | count
 constexpr int kLeafMask = 15;
 constexpr int kMaxBinLeaves = 16384;    // clusters a camera pose can sort (visibility_bins.cu)
-constexpr int kMaxClusterTris = 128;    // largest cluster of the binned visibility kernel
+constexpr int kMaxClusterTris = 256;    // largest cluster of the binned visibility kernel (maximal subtrees average ~0.6 of it)
 constexpr int kMaxDepth = 96;        // Karras tree over 63-bit Morton codes + 31-bit index tie-break: depth <= 96
 constexpr int kTileWords = 128;      // bitmap words per plan_reduce tile (one uint4 per lane)
 constexpr int kTileTris = kTileWords * 32;

@@ -48,7 +48,7 @@ constexpr int kFilterUnroll = IPP_FILTER_UNROLL;
 #endif
 constexpr int kSubRound = IPP_SUB_ROUND;  // staged triangles rasterised between two refreshes of the tile's depth bounds    // table loads a lane keeps in flight while a supertile's list is filtered
 static_assert(kBinRecords <= 65536, "tile-list entries carry 16 bits of record index");
-static_assert(kMaxClusterTris * 32 <= kBinRecords, "one chunk of 32 list entries must fit the record scratch");
+static_assert(kBinRecords >= 64, "a batch of set-up records ends at a round of 32 triangles and resumes there");
 
 struct __align__(16) BinShared {
     float t[kTilePixels];

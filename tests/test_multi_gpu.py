@@ -52,5 +52,17 @@ def test_two_ranks_share_the_edge_rendering(tmp_path, share):
                 assert all(int(res[r][name + "_memo"]) == distinct for r in range(2))
             else:
                 assert all(0 < x <= distinct for x in rendered) or distinct == 0
+        # [id, angleOffset] genes, the error path and a row pool that is far too small: same rows as one GPU with room for everything
+        g.clear_memo()
+        ang = [[[gene[0], 0.25 * ((gene[0] % 5) - 2)] for gene in p] for p in plans]
+        want_ang = g.evaluatePopulation(ang, True, True)
+        g.clear_memo()
+        want = g.evaluatePopulation(plans, True, True)
+        for r in range(2):
+            assert np.array_equal(res[r]["angles"], want_ang), r
+            assert int(res[r]["badid_raised"]) == 1, r
+            assert np.array_equal(res[r]["after_badid"], want), r
+            assert np.array_equal(res[r]["smallpool"], want) and np.array_equal(res[r]["smallpool_again"], want), r
+            assert int(res[r]["smallpool_evictions"]) > 0
     finally:
         g.close()
