@@ -65,6 +65,11 @@ double ipp_total_area(const ipp_t* h);
 double ipp_collision_penalty(const ipp_t* h);
 void ipp_scene_info(const ipp_t* h, double* center3, double* bbox6);
 void ipp_image_size(const ipp_t* h, int* width, int* height);
+/* The mesh ingest on its own (host code, no device needed): osgDB::readNodeFile + TriangleFunctor enumeration
+ * (SceneKeeper.cpp:73-86, :29): binary / ASCII .stl, .obj (Y-up -> Z-up, polygons fan-split) and the flat .ippm test format ->
+ * 9 floats per triangle in file order.  Call with out_Tx9 == NULL to obtain the count.  A file that cannot be read is an error
+ * (std::invalid_argument in the reference, SceneKeeper.cpp:79-82). */
+int ipp_load_mesh(const char* scene_path, float* out_Tx9, int64_t cap_triangles, int64_t* n_triangles);
 /* per-triangle Heron areas, file order (TriangleData.cpp:56-61) */
 int ipp_areas(const ipp_t* h, double* out_T);
 /* candidate viewpoint centres, N x 3 (PlanInterpreterBoxOrder::divideIntoBoxes :193-251) */

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "ipp_evaluate_population": (C.c_int, [H, c_i32p, c_f32p, c_i64p, C.c_int64, C.c_int, C.c_int, c_f64p, c_u32p]),
     "ipp_evaluate_population_device": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "ipp_update_memoised_edges": (C.c_int, [H, c_i32p, c_f32p, c_i64p, C.c_int64, c_i64p]),
+    "ipp_load_mesh": (C.c_int, [C.c_char_p, c_f32p, C.c_int64, c_i64p]),
     "ipp_memo_size": (C.c_int64, [H]),
     "ipp_evictions": (C.c_int64, [H]),
     "ipp_plan_reduce_variant": (C.c_char_p, [C.c_int]),

@@ -109,6 +109,17 @@ def _fp(a):
     return None if a is None else a.ctypes.data_as(_lib.c_f32p)
 
 
+def load_mesh(scene_file_name):
+    """The evaluator's mesh ingest on its own (host code): float32 [T, 3, 3], triangles in file order -- what
+    osgDB::readNodeFile + the TriangleFunctor enumeration hand to TriangleData (SceneKeeper.cpp:73-86, :29)."""
+    L = _lib.load()
+    n = C.c_int64()
+    _lib.check(L.ipp_load_mesh(os.fsencode(scene_file_name), None, 0, C.byref(n)))
+    out = np.zeros((int(n.value), 3, 3), dtype=np.float32)
+    _lib.check(L.ipp_load_mesh(os.fsencode(scene_file_name), out.ctypes.data_as(_lib.c_f32p), int(n.value), C.byref(n)))
+    return out
+
+
 class PlanCoverageEstimator(object):
     """PlanCoverageEstimator (cpp_binding.i:25-39; PlanCoverageEstimator.h:51-165)."""
 

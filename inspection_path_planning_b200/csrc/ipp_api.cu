@@ -5,6 +5,7 @@
 #include "../../include/ipp.h"
 #include "comm.h"
 #include "evaluator.h"
+#include "mesh_io.h"
 
 using ipp::Evaluator;
 
@@ -80,6 +81,14 @@ void ipp_scene_info(const ipp_t* h, double* center3, double* bbox6) {
 void ipp_image_size(const ipp_t* h, int* width, int* height) {
     *width = E(h).cam_.W;
     *height = E(h).cam_.H;
+}
+int ipp_load_mesh(const char* scene_path, float* out_Tx9, int64_t cap_triangles, int64_t* n_triangles) {
+    IPP_TRY
+    std::vector<float> tris;
+    ipp::load_mesh(scene_path, tris);
+    *n_triangles = (int64_t)(tris.size() / 9);
+    if (out_Tx9) memcpy(out_Tx9, tris.data(), (size_t)std::min<int64_t>(*n_triangles, cap_triangles) * 9 * sizeof(float));
+    IPP_CATCH
 }
 int ipp_areas(const ipp_t* h, double* out) {
     memcpy(out, E(h).areaHost_.data(), E(h).areaHost_.size() * sizeof(double));

@@ -68,10 +68,42 @@ class Parameters:
 
     @classmethod
     def from_python(cls, path):
-        """Reads a parameter file as multirun does (optimize_coverage.py:223-227); names this class does not know are ignored."""
-        scope = {}
+        """Reads a parameter file as multirun does (optimize_coverage.py:223-227): every top-level `NAME = value` whose value is a
+        literal, a name assigned earlier in the file (DOWN_CAM_ACTIVE = True ... [.., DOWN_CAM_ACTIVE]) or simple arithmetic on
+        those.  Nothing is executed: the reference's own settings/Parameters.py -- and the copy store_run_info leaves in
+        experiment_parameters/ -- starts with `import settings.Constants_and_Datastructures as const`; imports and any other
+        statement are skipped.  Names this class does not know are ignored."""
+        import ast
+        import operator
+        scope = {"True": True, "False": False, "None": None}
+        ops = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv, ast.FloorDiv: operator.floordiv,
+               ast.Mod: operator.mod, ast.Pow: operator.pow}
+
+        def ev(node):
+            if isinstance(node, ast.Constant):
+                return node.value
+            if isinstance(node, ast.Name):
+                return scope[node.id]
+            if isinstance(node, (ast.List, ast.Tuple)):
+                vals = [ev(e) for e in node.elts]
+                return vals if isinstance(node, ast.List) else tuple(vals)
+            if isinstance(node, ast.Dict):
+                return {ev(k): ev(v) for k, v in zip(node.keys, node.values)}
+            if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd, ast.Not)):
+                v = ev(node.operand)
+                return -v if isinstance(node.op, ast.USub) else (+v if isinstance(node.op, ast.UAdd) else (not v))
+            if isinstance(node, ast.BinOp) and type(node.op) in ops:
+                return ops[type(node.op)](ev(node.left), ev(node.right))
+            raise ValueError("not a literal")
+
         with open(path) as f:
-            exec(compile(f.read(), path, "exec"), {"__builtins__": {}}, scope)
+            tree = ast.parse(f.read(), path)
+        for stmt in tree.body:
+            if isinstance(stmt, ast.Assign) and len(stmt.targets) == 1 and isinstance(stmt.targets[0], ast.Name):
+                try:
+                    scope[stmt.targets[0].id] = ev(stmt.value)
+                except (ValueError, KeyError, TypeError, ZeroDivisionError):
+                    pass  # e.g. a value that needs the skipped import
         return cls(**{k: v for k, v in scope.items() if k.isupper() and hasattr(cls, k)})
 
 

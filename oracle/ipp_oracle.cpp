@@ -412,6 +412,7 @@ struct Oracle {
     // scratch item buffer
     std::vector<double> zbuf;
     std::vector<int32_t> idbuf;
+    std::vector<uint32_t> glDepth;  // depth model 1: 24-bit window depth per pixel
     std::vector<double> z1;  // edge-epsilon classification: per pixel and sample position
     std::vector<int32_t> idWide, idNarrow;
     size_t W32() const { return (T + 31) / 32; }
@@ -741,6 +742,14 @@ struct Oracle {
         double eps_px = 0.01;     // sample displacement in pixels
         double eps_depth = 1e-5;  // relative depth margin
     } margins;
+    // Depth model of the item buffer.  0 (default): planar depth, fragments within a relative 2^-16 of the nearest are ties, lowest
+    // ID wins (DEPTH_TIE_REL above).  1: the OpenGL depth buffer as the reference's viewer most likely had it (parity is unpinned:
+    // the GL driver is not in the reference tree) -- window depth z_w = f / (f - n) * (1 - n / z) of the perspective projection
+    // with n = zNear, f = zFar (UF/ImageViewerCaptureTool.cpp:22-27, no automatic near/far, :35-36), quantised to an unsigned
+    // 24-bit value, depth function GL_LESS with the triangles submitted in ID order (UF/TriangleData.cpp:93-106), cleared to 1.0,
+    // and the top-left fill rule for pixel centres exactly on an edge.  Used to bound what the choice of model can change
+    // (tests/test_oracle_known_answers.py, tools/depth_model_report.py); classification sets are only built for model 0.
+    int depthModel = 0;
 
     struct Cam {
         V3 eye, f, s, u;
@@ -849,6 +858,29 @@ struct Oracle {
         return true;
     }
 
+    // coverage with the top-left fill rule: a pixel centre exactly on an edge belongs to the triangle only if the edge is a left edge
+    // or a top edge (image y up), so that of two triangles that share the edge exactly one owns the pixel.  Edge functions are
+    // oriented so that the inside is positive.
+    static inline bool frag_top_left(const Setup& S, double X, double Y, double& t) {
+        double e[3] = {S.na[0] * X + S.na[1] * Y + S.na[2], S.nb[0] * X + S.nb[1] * Y + S.nb[2], S.nc[0] * X + S.nc[1] * Y + S.nc[2]};
+        const double* N[3] = {S.na, S.nb, S.nc};
+        double det = e[0] + e[1] + e[2];
+        if (det == 0) return false;
+        const double sg = det > 0 ? 1.0 : -1.0;  // all three edge functions carry the sign of det inside the triangle
+        for (int k = 0; k < 3; ++k) {
+            const double v = sg * e[k];
+            if (v < 0) return false;
+            if (v == 0) {
+                // the inward normal of the edge in the image plane is sg * (N[0], N[1]): a left edge has it pointing towards +x, a top
+                // edge (horizontal, interior below it) towards -y
+                const double nx = sg * N[k][0], ny = sg * N[k][1];
+                if (!(nx > 0 || (nx == 0 && ny < 0))) return false;
+            }
+        }
+        t = S.vol / det;
+        return true;
+    }
+
     // Columns [xa, xb] of image row Y (inside [x0, x1]) outside which no pixel centre can pass the coverage test of frag() or
     // frag_dilated(): a pure accelerator of the loops below (long thin triangles have bounding boxes hundreds of times their
     // area), the per-pixel tests are unchanged.  Conservative: every edge function may miss its sign by `slack` image-plane units
@@ -891,6 +923,38 @@ struct Oracle {
         std::fill(zbuf.begin(), zbuf.begin() + NP, INFINITY);
         std::fill(idbuf.begin(), idbuf.begin() + NP, -1);
         Setup S;
+        if (depthModel == 1) {
+            // OpenGL-style: one pass in ID order, 24-bit window depth, LESS
+            const double fn = zFar / (zFar - zNear);
+            const double dmax = 16777215.0;  // 2^24 - 1
+            std::vector<uint32_t>& dbuf = glDepth;
+            dbuf.assign(NP, 16777215u);
+            for (size_t i = 0; i < T; ++i) {
+                setup_tri(cam, i, S);
+                if (!S.ok) continue;
+                for (int py = S.y0; py <= S.y1; ++py) {
+                    double Y = ((py + 0.5) / H * 2.0 - 1.0) * cam.tanY;
+                    int xa, xb;
+                    if (!row_span(S, cam, Y, 0.0, S.x0, S.x1, xa, xb)) continue;
+                    for (int px = xa; px <= xb; ++px) {
+                        double X = ((px + 0.5) / W * 2.0 - 1.0) * cam.tanX;
+                        double t;
+                        if (!frag_top_left(S, X, Y, t)) continue;
+                        if (!(t >= zNear && t <= zFar)) continue;  // clip to the view volume
+                        const double zw = fn * (1.0 - zNear / t);
+                        const uint32_t d = (uint32_t)std::floor(std::min(std::max(zw, 0.0), 1.0) * dmax + 0.5);
+                        size_t pix = (size_t)py * W + px;
+                        if (d < dbuf[pix]) {
+                            dbuf[pix] = d;
+                            idbuf[pix] = (int32_t)i;
+                        }
+                    }
+                }
+            }
+            for (size_t p = 0; p < NP; ++p)
+                if (idbuf[p] >= 0) bits_set(seen, (size_t)idbuf[p]);
+            return;
+        }
         // pass 1: nearest depth per pixel; pass 2: lowest ID within the depth-tie band of the nearest (see DEPTH_TIE_REL)
         for (int pass = 0; pass < 2; ++pass) {
             for (size_t i = 0; i < T; ++i) {
@@ -1292,6 +1356,7 @@ void oracle_set_margins(void* h, double eps_px, double eps_depth) {
     o->margins.eps_px = eps_px;
     o->margins.eps_depth = eps_depth;
 }
+void oracle_set_depth_model(void* h, int model) { ((Oracle*)h)->depthModel = model; }
 void oracle_counters(void* h, uint64_t* out3) {
     Oracle* o = (Oracle*)h;
     out3[0] = o->nSnapshots; out3[1] = o->nPixels; out3[2] = o->nCollisionQueries;

@@ -256,6 +256,12 @@ class Oracle:
     def set_margins(self, eps_px, eps_depth):
         self._L.oracle_set_margins(self._h, C.c_double(eps_px), C.c_double(eps_depth))
 
+    def set_depth_model(self, model):
+        """0: planar depth, relative 2^-16 tie band, lowest ID (default).  1: OpenGL-style 24-bit window depth, GL_LESS in ID order,
+        top-left fill rule (see ipp_oracle.cpp).  Clears the memo: its bitmaps belong to the model they were rendered with."""
+        self._L.oracle_set_depth_model(self._h, int(model))
+        self.updateMemoisedEdges([])
+
     def counters(self):
         out = np.zeros(3, dtype=np.uint64)
         self._L.oracle_counters(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)))
