@@ -683,10 +683,11 @@ def run_gpu(args):
                 "note": "algorithmic bytes = 8 B per cluster-table entry and 4 B per tile-list entry scanned + 48 B per triangle set up or "
                         "staged (device counters of the timed launches); they are served by L1/L2"},
         "profile_source": facts.get("source"),
-        "note": "K4 is bound by instruction issue (ncu: ~65 %% of the issue slots busy at 20 warps per SM, no memory level above 10 %% of its "
-                "peak), not by HBM: frac = warp instructions per second / (148 x 4 x SM clock).  Warp instructions, L2 bytes and DRAM bytes "
-                "per rasterised tile come from the committed ncu capture of this kernel on this workload (profile_source); tiles per launch "
-                "and the launch time are measured live (device counter, CUDA events on the evaluator's stream)."}
+        "note": "K4 is bound by instruction issue (ncu capture named in profile_source: %.1f %% of the issue slots busy at %.0f %% of the warp "
+                "slots, L2 at ~11 %% and DRAM at ~4 %% of their peaks), not by HBM: frac = warp instructions per second / (148 x 4 x SM "
+                "clock).  Warp instructions, L2 bytes and DRAM bytes per rasterised tile come from that committed capture of this kernel on "
+                "this workload; tiles per launch and the launch time are measured live (device counter, CUDA events on the evaluator's "
+                "stream)." % (facts.get(kname + "_issue_active_pct", float("nan")), facts.get(kname + "_warps_active_pct", float("nan")))}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
