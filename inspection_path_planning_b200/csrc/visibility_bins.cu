@@ -463,6 +463,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                         const unsigned m = __ballot_sync(0xffffffffu, hit);
                         if (m == 0u) continue;
                         myTris += __popc(m);
+                        // the record is staged a few header chunks from now: have it in L1 by then (A/B: -0.9 % on config 2, -1.2 % on luis4)
+                        if (hit) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)i * 4));
                         if (hit) q16[nq + __popc(m & ltMask)] = (uint16_t)i;
                         nq += __popc(m);
                         __syncwarp();

@@ -38,7 +38,9 @@ for it in range(3):
             print("   per tile: triangles surviving set-up %.1f, %.1f %% of the tiles stay open" % (
                 vs["live_triangles"] / vs["tiles"], 100.0 * vs["open_tiles"] / vs["tiles"]), flush=True)
     kt = {names[k]: g.kernel_time(k) for k in range(6)}
-    print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  counters %s" % (it, dt, pop / dt, (1 - fit[:, 0]).mean(), c), flush=True)
+    import hashlib
+    print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  fitness sha1 %s  counters %s" % (
+        it, dt, pop / dt, (1 - fit[:, 0]).mean(), hashlib.sha1(np.ascontiguousarray(fit).tobytes()).hexdigest()[:12], c), flush=True)
     print("   kernel ms:", {k: (round(v[0], 3), v[1]) for k, v in kt.items()}, flush=True)
     if c["rays"]:
         print("   rays/s (visibility kernel) %.3e" % (c["rays"] / (kt["visibility"][0] * 1e-3)), flush=True)
