@@ -70,11 +70,11 @@ __device__ __forceinline__ bool box_may_hit(const PlaneD pl[6], const double lo[
     return true;
 }
 
-__device__ bool polytope_hits_mesh(const DeviceScene& sc, const PlaneD pl[6], const double lo[3], const double hi[3]) {
+__device__ bool polytope_hits_mesh(const DeviceScene& sc, const PlaneD pl[6], const double lo[3], const double hi[3], int root = 0) {
     if (sc.T == 0) return false;
     int stack[kMaxDepth];
     int sp = 0;
-    int node = 0;
+    int node = root;
     while (true) {
         const BvhNode* np = sc.nodes + node;
         float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
@@ -122,6 +122,79 @@ __global__ void k_collide_keys(DeviceScene sc, const int* __restrict__ keys, int
     }
     coll[key] = r;
 }
+// The same query with one warp per key, for the launches that have only a handful of keys (a generation of an NSGA-II run brings a
+// few new edges at a time, and one thread walking the BVH alone is all such a launch would last): the warp keeps a frontier of
+// BVH nodes in shared memory, every lane takes one node per round, tests both child boxes, tests the triangles of a leaf child
+// itself and pushes an inner child back.  Any-hit: the answer does not depend on the order, so it is the one-thread answer.
+constexpr int kCollideWarps = 4;
+constexpr int kFrontierCap = 512;
+__global__ void __launch_bounds__(kCollideWarps * 32) k_collide_keys_warp(DeviceScene sc, const int* __restrict__ keys, int n,
+                                                                          const double* __restrict__ pos, int N, uint8_t* __restrict__ coll) {
+    __shared__ int s_frontier[kCollideWarps][kFrontierCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kCollideWarps + warp;
+    if (i >= n) return;
+    const int key = keys[i];
+    const int a = key / N, b = key - a * N;
+    const D3 A = d3(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2]), B = d3(pos[3 * b], pos[3 * b + 1], pos[3 * b + 2]);
+    bool found = false;
+    if (!equal(A, B) && sc.T > 0) {
+        PlaneD pl[6];
+        double lo[3], hi[3];
+        edge_prism(A, B, pl, lo, hi);
+        int* fr = s_frontier[warp];
+        if (lane == 0) fr[0] = 0;
+        int count = 1;
+        __syncwarp();
+        while (count > 0 && !found) {
+            const int take = min(count, 32);
+            const int node = lane < take ? fr[count - 1 - lane] : -1;
+            count -= take;
+            __syncwarp();
+            int child[2] = {-1, -1};
+            bool hit = false;
+            if (node >= 0) {
+                const BvhNode* np = sc.nodes + node;
+                const float4 q0 = __ldg(&np->q0), q1 = __ldg(&np->q1), q2 = __ldg(&np->q2), q3 = __ldg(&np->q3);
+                const int link[2] = {__float_as_int(q3.x), __float_as_int(q3.y)};
+                const bool bh[2] = {box_may_hit(pl, lo, hi, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y),
+                                    box_may_hit(pl, lo, hi, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w)};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (!bh[c]) continue;
+                    if (link[c] < 0) {
+                        const int code = ~link[c];
+                        const int first = code >> kLeafShift, cnt = code & kLeafMask;
+                        for (int k = 0; k < cnt && !hit; ++k) {
+                            const float4 va = __ldg(sc.oa + first + k), vb = __ldg(sc.ob + first + k), vc = __ldg(sc.oc + first + k);
+                            hit = polytope_hits_triangle(pl, d3(va.x, va.y, va.z), d3(vb.x, vb.y, vb.z), d3(vc.x, vc.y, vc.z));
+                        }
+                    } else {
+                        child[c] = link[c];
+                    }
+                }
+            }
+            found = __any_sync(0xffffffffu, hit);
+            if (found) break;
+            // push the inner children; a frontier that would overflow is walked by its lanes on their own instead
+            const unsigned m0 = __ballot_sync(0xffffffffu, child[0] >= 0), m1 = __ballot_sync(0xffffffffu, child[1] >= 0);
+            const int add = __popc(m0) + __popc(m1);
+            if (count + add > kFrontierCap) {
+                bool h = false;
+                if (child[0] >= 0) h = polytope_hits_mesh(sc, pl, lo, hi, child[0]);
+                if (!h && child[1] >= 0) h = polytope_hits_mesh(sc, pl, lo, hi, child[1]);
+                found = __any_sync(0xffffffffu, h);
+            } else {
+                const unsigned lt = (1u << lane) - 1u;
+                if (child[0] >= 0) fr[count + __popc(m0 & lt)] = child[0];
+                if (child[1] >= 0) fr[count + __popc(m0) + __popc(m1 & lt)] = child[1];
+                count += add;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) coll[key] = found ? 1 : 0;
+}
 __global__ void k_collide_xyz(DeviceScene sc, const double* __restrict__ edges, int64_t n, uint8_t* __restrict__ out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -142,7 +215,10 @@ __global__ void k_boxes_hit(DeviceScene sc, const double* __restrict__ centres, 
 }
 
 void launch_collide_keys(const DeviceScene& sc, const int* d_keys, int n, const double* d_pos, int N, uint8_t* d_coll, cudaStream_t st) {
-    if (n > 0) k_collide_keys<<<(n + 63) / 64, 64, 0, st>>>(sc, d_keys, n, d_pos, N, d_coll);
+    if (n <= 0) return;
+    // a few keys: a warp each (same answers, a fraction of the latency); many: a thread each fills the machine
+    if (n <= 2048) k_collide_keys_warp<<<(n + kCollideWarps - 1) / kCollideWarps, kCollideWarps * 32, 0, st>>>(sc, d_keys, n, d_pos, N, d_coll);
+    else k_collide_keys<<<(n + 63) / 64, 64, 0, st>>>(sc, d_keys, n, d_pos, N, d_coll);
 }
 void launch_collide_xyz(const DeviceScene& sc, const double* d_edges, int64_t n, uint8_t* d_out, cudaStream_t st) {
     if (n > 0) k_collide_xyz<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(sc, d_edges, n, d_out);

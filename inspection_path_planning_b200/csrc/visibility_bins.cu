@@ -20,6 +20,8 @@
 //
 // Used when the mesh has <= kMaxBinLeaves clusters of <= kMaxClusterTris triangles (meshes up to ~2 M triangles) and the image is
 // <= 1024 pixels a side; other inputs take the BVH-walking kernel of visibility.cu.
+#include <cstdlib>
+
 #include <cub/block/block_radix_sort.cuh>
 
 #include "raster.cuh"
@@ -221,7 +223,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                                                                  const int* __restrict__ tableCount, const uint32_t* __restrict__ tileMask,
                                                                  const unsigned long long* __restrict__ superMask,
                                                                  unsigned long long* scratch, float4* recordsAll, uint8_t* __restrict__ flags,
-                                                                 const int* __restrict__ slotList, int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters) {
+                                                                 const int* __restrict__ slotList, int32_t* __restrict__ idImage, unsigned long long* __restrict__ counters,
+                                                                 int splitLog2) {
     __shared__ BinShared s_all[kBinWarps];
     const int warp = threadIdx.x >> 5;
     int lane;
@@ -237,7 +240,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
     const float zNear = cam.zNear, zFar = cam.zFar;
     const float iq = (zFar * kDepthTie * 1.000001f + 1e-4f) / 65535.f;  // depth of a quantised table entry (a lower bound)
-    const long long totalSuper = (long long)__ldg(superOffset + nSnaps);
+    // a task = one occupied supertile, or -- when a launch has too few of them to fill the grid (the small batches of an NSGA-II
+    // generation) -- one quadrant (splitLog2 = 2) or one tile (4) of it: the same work in finer pieces
+    const long long totalSuper = (long long)__ldg(superOffset + nSnaps) << splitLog2;
     const unsigned ltMask = (1u << lane) - 1u;
 
     while (true) {
@@ -245,6 +250,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         if (lane == 0) task = (long long)atomicAdd(&counters[1], 1ull);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= totalSuper) break;
+        const unsigned part = (unsigned)task & ((1u << splitLog2) - 1u);
+        task >>= splitLog2;
         const int si = find_snapshot(superOffset, nSnaps, task, lane);
         __syncwarp();
         {
@@ -298,7 +305,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         const float zFarCull = zFar * kDepthTie;
 
         // ---- regions of the supertile: the whole of it, or, when its triangles do not fit the record scratch, halves of it ----
-        unsigned long long stack = (unsigned long long)region_pack(0, 3, 0, 3);
+        unsigned long long stack = (unsigned long long)(splitLog2 == 0   ? region_pack(0, 3, 0, 3)
+                                                        : splitLog2 == 2 ? region_pack(2 * (part & 1u), 2 * (part & 1u) + 1, 2 * (part >> 1), 2 * (part >> 1) + 1)
+                                                                         : region_pack(part & 3u, part & 3u, part >> 2, part >> 2));
         int depth = 1;
         mySuperRec++;
         while (depth > 0) {
@@ -576,12 +585,22 @@ void launch_visibility_bins(const DeviceScene& sc, const CameraParams& cam, cons
                             int64_t totalSuper, const BinBuffers& b, uint8_t* d_flags, const int* d_slotList, int32_t* d_idImage,
                             unsigned long long* d_counters, cudaStream_t st) {
     if (totalSuper <= 0 || nSnaps <= 0) return;
-    long long groups = (totalSuper + kBinWarps - 1) / kBinWarps;
+    // fewer supertiles than two per resident warp: hand them out as quadrants or single tiles (a supertile is up to 16 tiles of serial
+    // work for one warp, which is all a small launch would last).  The pieces repeat the table filter and part of the set-up, so
+    // this only pays while most warps would otherwise idle -- measured on luis4: 60 poses 3.0 -> 1.3 ms as single tiles, 300 poses
+    // 4.4 ms whole against 5.0 ms as quadrants, 1 500 poses 13.8 / 14.3 / 23.4 ms whole / quadrants / tiles.
+    const long long warps = (long long)b.gridBlocks * kBinWarps;
+    int splitLog2 = totalSuper >= 2 * warps ? 0 : (totalSuper * 4 >= 2 * warps ? 2 : 4);
+    if (const char* e = getenv("IPP_BINS_SPLIT")) {  // tests and A/B runs: 0, 2 or 4
+        const int v = atoi(e);
+        if (v == 0 || v == 2 || v == 4) splitLog2 = v;
+    }
+    long long groups = ((totalSuper << splitLog2) + kBinWarps - 1) / kBinWarps;
     int grid = (int)std::min<long long>(b.gridBlocks, groups);
     // counters[1] is the work cursor of this launch
     cudaMemsetAsync(d_counters + 1, 0, sizeof(unsigned long long), st);
     k_visibility_bins<<<grid, kBinThreads, 0, st>>>(sc, cam, d_snaps, d_superOffset, nSnaps, b.table, b.stride, b.tableCount, b.tileMask,
-                                                   b.superMask, b.scratch, b.records, d_flags, d_slotList, d_idImage, d_counters);
+                                                   b.superMask, b.scratch, b.records, d_flags, d_slotList, d_idImage, d_counters, splitLog2);
 }
 
 }  // namespace ipp

@@ -618,6 +618,33 @@ def test_render_batches_split_by_pose_budget_give_identical_results(monkeypatch)
         b.close()
 
 
+@pytest.mark.parametrize("mesh", ["mockup_only", "luis4"])
+def test_supertile_task_granularity_does_not_change_results(mesh, monkeypatch):
+    """A launch with few occupied supertiles hands them out as quadrants or single tiles (the small calls of an NSGA-II generation,
+    csrc/visibility_bins.cu launch_visibility_bins); IPP_BINS_SPLIT forces each granularity on the same edges at 1024 x 1024: same
+    edge bitmaps and fitness rows, bit for bit."""
+    from inspection_path_planning_b200 import cpp_binding
+    g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), specs(1024))
+    try:
+        rng = np.random.default_rng(77)
+        plans = random_plans(rng, g.getNumberOfBoxes(), 6, (2, 5))
+        edges = [(p[k][0], p[k + 1][0]) for p in plans for k in range(len(p) - 1)][:8]
+        ref_fit = ref_maps = None
+        for split in ("0", "2", "4"):
+            monkeypatch.setenv("IPP_BINS_SPLIT", split)
+            g.updateMemoisedEdges([])
+            fit = g.evaluatePopulation(plans, True, True)
+            maps = [g.edge_bitmap(a, b) for a, b in edges]
+            if ref_fit is None:
+                ref_fit, ref_maps = fit, maps
+                assert any(popcount(m) > 0 for m in maps)
+            else:
+                assert np.array_equal(fit, ref_fit), split
+                assert all(np.array_equal(m, r) for m, r in zip(maps, ref_maps)), split
+    finally:
+        g.close()
+
+
 def test_images_above_1024_pixels_take_the_bvh_walk(oracle_mod):
     from inspection_path_planning_b200 import cpp_binding
     sp = specs(1100)
