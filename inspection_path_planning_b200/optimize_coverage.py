@@ -145,33 +145,33 @@ def dominates(a, b):
 # DEAP pieces
 # ---------------------------------------------------------------------------------------------------------------------
 def sort_nondominated(individuals):
-    """Fast non-dominated sort (Deb 2002); individuals with equal fitness share a front, as in tools.sortNondominated."""
+    """Fast non-dominated sort (Deb 2002); individuals with equal fitness share a front, as in tools.sortNondominated.  The
+    dominance relation of the distinct fitness values is one numpy comparison; fronts and the order inside them are the ones the
+    pairwise loop of the textbook algorithm produces (first front in order of appearance, then every value when its last
+    dominator of the previous front has been taken, dominated values in order of appearance)."""
     by_fit = {}
     for ind in individuals:
         by_fit.setdefault(tuple(ind.fitness), []).append(ind)
     fits = list(by_fit)
-    dominated_by = {f: [] for f in fits}
-    n_dom = {f: 0 for f in fits}
-    current = []
-    for i, fi in enumerate(fits):
-        for fj in fits[i + 1:]:
-            if dominates(fi, fj):
-                n_dom[fj] += 1
-                dominated_by[fi].append(fj)
-            elif dominates(fj, fi):
-                n_dom[fi] += 1
-                dominated_by[fj].append(fi)
-        if n_dom[fi] == 0:
-            current.append(fi)
+    if not fits:
+        return []
+    f = np.asarray(fits, dtype=np.float64)
+    le = (f[:, None, :] <= f[None, :, :]).all(axis=2)
+    lt = (f[:, None, :] < f[None, :, :]).any(axis=2)
+    dom = le & lt  # dom[i, j]: value i dominates value j
+    n_dom = dom.sum(axis=0)
+    current = np.nonzero(n_dom == 0)[0]
+    done = np.zeros(len(fits), dtype=bool)
     fronts = []
-    while current:
-        fronts.append([ind for f in current for ind in by_fit[f]])
-        nxt = []
-        for f in current:
-            for g in dominated_by[f]:
-                n_dom[g] -= 1
-                if n_dom[g] == 0:
-                    nxt.append(g)
+    while current.size:
+        fronts.append([ind for i in current for ind in by_fit[fits[i]]])
+        done[current] = True
+        sub = dom[current]
+        n_dom = n_dom - sub.sum(axis=0)
+        nxt = np.nonzero((n_dom == 0) & ~done)[0]
+        if nxt.size:
+            last = sub.shape[0] - 1 - np.argmax(sub[::-1, nxt], axis=0)  # position in `current` of the last dominator
+            nxt = nxt[np.lexsort((nxt, last))]
         current = nxt
     return fronts
 
@@ -253,6 +253,11 @@ class ParetoFront:
 
     def update(self, population):
         for ind in population:
+            # an individual this front has already been offered is either in it or dominated by it, and stays so: skip
+            # (the flag is not cloned: offspring are offered again)
+            if getattr(ind, "_offered_to", None) is self:
+                continue
+            ind._offered_to = self
             dominated = False
             same = False
             keep = []

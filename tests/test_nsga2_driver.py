@@ -60,6 +60,55 @@ def test_tournament_and_crossover():
     assert sorted(g[0] for g in a + b) == before and len(a) + len(b) == 8
 
 
+def test_vectorised_front_sort_keeps_the_order_of_the_pairwise_algorithm():
+    """sort_nondominated builds the dominance relation with numpy; fronts and the order inside them (which decides who survives
+    a crowding-distance tie and how selTournamentDCD pairs the survivors) must be those of the pairwise loop of tools.sortNondominated."""
+    import random
+
+    def pairwise(individuals):
+        by_fit = {}
+        for ind in individuals:
+            by_fit.setdefault(tuple(ind.fitness), []).append(ind)
+        fits = list(by_fit)
+        dominated_by = {f: [] for f in fits}
+        n_dom = {f: 0 for f in fits}
+        current = []
+        for i, fi in enumerate(fits):
+            for fj in fits[i + 1:]:
+                if oc.dominates(fi, fj):
+                    n_dom[fj] += 1
+                    dominated_by[fi].append(fj)
+                elif oc.dominates(fj, fi):
+                    n_dom[fi] += 1
+                    dominated_by[fj].append(fi)
+            if n_dom[fi] == 0:
+                current.append(fi)
+        fronts = []
+        while current:
+            fronts.append([ind for f in current for ind in by_fit[f]])
+            nxt = []
+            for f in current:
+                for g in dominated_by[f]:
+                    n_dom[g] -= 1
+                    if n_dom[g] == 0:
+                        nxt.append(g)
+            current = nxt
+        return fronts
+
+    rng = random.Random(3)
+    for _ in range(60):
+        n = rng.randint(1, 90)
+        inds = []
+        for i in range(n):
+            ind = oc.Individual([[i]])
+            ind.fitness = (rng.randint(0, 10) / 10.0, float(rng.randint(0, 12)))
+            inds.append(ind)
+        got = [[x[0][0] for x in f] for f in oc.sort_nondominated(inds)]
+        want = [[x[0][0] for x in f] for f in pairwise(inds)]
+        assert got == want
+    assert oc.sort_nondominated([]) == []
+
+
 def test_pareto_front_keeps_only_non_dominated_and_no_duplicates():
     pf = oc.ParetoFront()
     pf.update([_ind((0.5, 5.0)), _ind((0.6, 6.0)), _ind((0.4, 7.0))])
