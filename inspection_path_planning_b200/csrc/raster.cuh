@@ -94,7 +94,14 @@ __device__ __forceinline__ void tile_init(float* __restrict__ St, int* __restric
 struct SuperGeom {
     float X0, Y0;    // image-plane coordinates of the supertile's first pixel centre
     float ipx, ipy;  // pixels per image-plane unit
+    // extreme pixel centres of the supertile's four tile columns ([c] = min, [4 + c] = max) and rows, the very values
+    // tile_geometry() gives a tile (tXmin, tXmax, tYmin, tYmax); nullptr: the screen-box mask is not refined
+    const float* tX = nullptr;
+    const float* tY = nullptr;
 };
+#ifndef IPP_EXACT_TILE_MASK
+#define IPP_EXACT_TILE_MASK 1
+#endif
 constexpr float kBoxPadPx = 0.5f;
 template <bool kPoseOnly>
 __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
@@ -151,6 +158,31 @@ __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Sn
                     if (c0 <= c1 && r0 <= r1)
                         tiles = (((2u << c1) - (1u << c0)) * 0x1111u) & ((16u << (4 * r1)) - 1u) & ~((1u << (4 * r0)) - 1u);
                 }
+#if IPP_EXACT_TILE_MASK
+                if (super->tX && tiles != 0u) {
+                    // ... and of those, the tiles that pass the tile-level edge test stage_record() would apply (same expressions, same
+                    // bits): a long thin triangle touches a fraction of the tiles of its screen box, and every tile left in the mask
+                    // fetches the record, stages it and throws it away
+                    unsigned exact = 0u;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (((tiles >> (4 * r)) & 0xfu) == 0u) continue;
+                        const float Ymin = super->tY[r], Ymax = super->tY[4 + r];
+                        const float ia = __fmaf_rn(o[2], o[2] >= 0.f ? Ymax : Ymin, o[0]);
+                        const float ib = __fmaf_rn(o[5], o[5] >= 0.f ? Ymax : Ymin, o[3]);
+                        const float ic = __fmaf_rn(o[8], o[8] >= 0.f ? Ymax : Ymin, o[6]);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float Xmin = super->tX[c], Xmax = super->tX[4 + c];
+                            const float ma = __fmaf_rn(o[1], o[1] >= 0.f ? Xmax : Xmin, ia);
+                            const float mb = __fmaf_rn(o[4], o[4] >= 0.f ? Xmax : Xmin, ib);
+                            const float mc = __fmaf_rn(o[7], o[7] >= 0.f ? Xmax : Xmin, ic);
+                            if (fminf(fminf(ma, mb), mc) >= 0.f) exact |= 1u << (4 * r + c);
+                        }
+                    }
+                    tiles &= exact;
+                }
+#endif
                 *tilesOut = tiles;
             } else {
             // can any pixel centre of the tile be inside?  Each edge function is monotone in X and in Y (also as computed), so its
@@ -196,7 +228,7 @@ __device__ __forceinline__ bool stage_record(const float4* r, float* __restrict_
 // as computed (explicit fmaf), so the block rejection is exact.  Returns true when some hit changed.
 __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__restrict__ tri)[kTriWords], float* __restrict__ St,
                                               int* __restrict__ Sid, const TileGeom& g, int lane, float zNear, float zFar, float zcull,
-                                              float bz) {
+                                              float bz, unsigned* diagBlocks = nullptr) {
     bool dirty = false;
     while (live) {
         const int k = __ffs(live) - 1;
@@ -217,6 +249,7 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
                            2e-6f * (fabsf(gs) + fabsf(gu) + fabsf(gf));
         const float zloBlk = fmaxf(zloTri, vol * rcp_approx(dmax) * 0.9999f);
         unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && dmax > 0.f && zloBlk <= bz);
+        if (diagBlocks) *diagBlocks += __popc(todo);
         // kBlocksPerStep blocks per step: their tests are independent (different pixels), which hides the latency of one behind
         // the others
         while (todo) {

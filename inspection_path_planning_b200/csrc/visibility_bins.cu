@@ -38,7 +38,7 @@ constexpr unsigned long long kNoEntry = ~0ull;
 constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
 constexpr int kBinRecords = 4096;   // set-up triangles (64 B each) a warp can keep for one supertile (or part of one)
 #ifndef IPP_STAGE_MIN
-#define IPP_STAGE_MIN 8
+#define IPP_STAGE_MIN 1
 #endif
 constexpr int kStageMin = IPP_STAGE_MIN;  // waiting records that make a staging round worth running at the end of a header chunk
 #ifndef IPP_FILTER_UNROLL
@@ -46,7 +46,7 @@ constexpr int kStageMin = IPP_STAGE_MIN;  // waiting records that make a staging
 #endif
 constexpr int kFilterUnroll = IPP_FILTER_UNROLL;
 #ifndef IPP_SUB_ROUND
-#define IPP_SUB_ROUND 16
+#define IPP_SUB_ROUND 8
 #endif
 constexpr int kSubRound = IPP_SUB_ROUND;  // staged triangles rasterised between two refreshes of the tile's depth bounds    // table loads a lane keeps in flight while a supertile's list is filtered
 static_assert(kBinRecords <= 65536, "tile-list entries carry 16 bits of record index");
@@ -57,6 +57,7 @@ struct __align__(16) BinShared {
     int id[kTilePixels];
     float tri[kPending][kTriWords];
     uint16_t queue[96];  // records of the tile being rasterised that wait for a staging round
+    float tileX[8], tileY[8];  // extreme pixel centres of the supertile's tile columns and rows ([k] min, [4 + k] max)
     Snapshot snap;
 };
 
@@ -236,6 +237,9 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
     uint16_t* q16 = S.queue;
     unsigned long long myRays = 0, myEntries = 0;
     unsigned myTris = 0, myTiles = 0, mySuperRec = 0, mySuperSplit = 0;  // statistics (lane 0 only matters)
+#ifdef IPP_VIS_DIAG
+    unsigned long long dLive = 0, dOpen = 0, dBlocks = 0, dStaged = 0;  // instrumented builds only (tools/build_variant.py -DIPP_VIS_DIAG)
+#endif
     const float kx = (float)(2.0 * cam.tanX / cam.W), cx = (float)((1.0 / cam.W - 1.0) * cam.tanX);
     const float ky = (float)(2.0 * cam.tanY / cam.H), cy = (float)((1.0 / cam.H - 1.0) * cam.tanY);
     const float zNear = cam.zNear, zFar = cam.zFar;
@@ -302,6 +306,19 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         sgm.Y0 = __fmaf_rn((float)((int)ssy * 4 * kTile), ky, cy);
         sgm.ipx = 1.f / kx;
         sgm.ipy = 1.f / ky;
+        if (lane < 16) {
+            // the expressions of tile_geometry(): tXmin / tYmin, and tXmax / tYmax through the last 8x4 block of the tile
+            const int k = lane & 3;
+            const bool isY = (lane & 8) != 0, isMax = (lane & 4) != 0;
+            const int p0 = ((int)(isY ? ssy : ssx) * 4 + k) * kTile;
+            const float kk = isY ? ky : kx, cc = isY ? cy : cx;
+            const float lo = __fmaf_rn((float)p0, kk, cc);
+            const float hi = isY ? __fmaf_rn(7.f, 4.f * ky, __fmaf_rn((float)(p0 + 3), ky, cy)) : __fmaf_rn(3.f, 8.f * kx, __fmaf_rn((float)(p0 + 7), kx, cx));
+            (isY ? S.tileY : S.tileX)[(isMax ? 4 : 0) + k] = isMax ? hi : lo;
+        }
+        sgm.tX = S.tileX;
+        sgm.tY = S.tileY;
+        __syncwarp();
         const float zFarCull = zFar * kDepthTie;
 
         // ---- regions of the supertile: the whole of it, or, when its triangles do not fit the record scratch, halves of it ----
@@ -434,6 +451,14 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                         bool mineOk = false;
                         if (mineValid) mineOk = stage_record(rec + (size_t)myRec * 4, S.tri[lane], zcull, tg);
                         const unsigned live = __ballot_sync(0xffffffffu, mineOk);  // triangles that can produce a fragment in this tile
+#ifdef IPP_VIS_DIAG
+                        dLive += __popc(live);
+                        dStaged += __popc(__ballot_sync(0xffffffffu, mineValid));
+#if IPP_VIS_DIAG == 2
+                        // how many of the rejected ones fall to the depth test alone (reported instead of the open tiles)
+                        dOpen += __popc(__ballot_sync(0xffffffffu, mineValid && !mineOk && rec[(size_t)myRec * 4 + 3].z > zcull * 1.000001f));
+#endif
+#endif
                         if (live) {
                             if (!inited) {
                                 tile_init(S.t, S.id, lane, vw, vh, zFar);
@@ -446,7 +471,13 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                             for (int s0 = 0; s0 < 32; s0 += kSubRound) {
                                 const unsigned sub = live & (kSubRound >= 32 ? 0xffffffffu : (((1u << (kSubRound & 31)) - 1u) << s0));
                                 if (sub == 0u) continue;
+#ifdef IPP_VIS_DIAG
+                                unsigned nb = 0;
+                                const bool dirty = raster_staged(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg, &nb);
+                                dBlocks += nb;
+#else
                                 const bool dirty = raster_staged(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
+#endif
                                 if (__any_sync(0xffffffffu, dirty)) {
                                     tileHit = true;
                                     __syncwarp();
@@ -494,6 +525,11 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                     if (nq > 0) flush(lane < nq, q16[lane]);
                     __syncwarp();
                     zcullKeep = zcull;
+#ifdef IPP_VIS_DIAG
+#if IPP_VIS_DIAG != 2
+                    if (zcull >= zFarCull) dOpen++;
+#endif
+#endif
                     if (single && overflow) continue;  // more batches of this tile's triangles follow
                     // ---- the winners ----
                     if (idImage && !inited) tile_init(S.t, S.id, lane, vw, vh, zFar);  // test hook: background pixels are reported too
@@ -523,8 +559,15 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
         atomicAdd(&counters[3], (unsigned long long)myTris);
         atomicAdd(&counters[4], (unsigned long long)myTiles);
         atomicAdd(&counters[5], myEntries);
+#ifdef IPP_VIS_DIAG
+        atomicAdd(&counters[6], dLive);
+        atomicAdd(&counters[7], dOpen);
+        atomicAdd(&counters[8], dBlocks);   // reported as "supertiles" by ipp_visibility_stats in such a build
+        atomicAdd(&counters[9], dStaged);   // ... and "supertile_splits"
+#else
         atomicAdd(&counters[8], (unsigned long long)mySuperRec);
         atomicAdd(&counters[9], (unsigned long long)mySuperSplit);
+#endif
     }
 }
 

@@ -34,9 +34,10 @@ for it in range(3):
     vs = g.visibility_stats()
     if vs["tiles"]:
         print("   per tile: nodes %.1f triangles %.1f (tiles %d)" % (vs["nodes"] / vs["tiles"], vs["triangles"] / vs["tiles"], vs["tiles"]), flush=True)
-        if vs["live_triangles"]:  # library built with -DIPP_VIS_DIAG
-            print("   per tile: triangles surviving set-up %.1f, %.1f %% of the tiles stay open" % (
-                vs["live_triangles"] / vs["tiles"], 100.0 * vs["open_tiles"] / vs["tiles"]), flush=True)
+        if vs["live_triangles"]:  # library built with -DIPP_VIS_DIAG (tools/build_variant.py)
+            print("   per tile: records staged %.1f, live after the tile test %.1f, 8x4 block tests %.1f, %.1f %% of the tiles stay open" % (
+                vs["supertile_splits"] / vs["tiles"], vs["live_triangles"] / vs["tiles"], vs["supertiles"] / vs["tiles"],
+                100.0 * vs["open_tiles"] / vs["tiles"]), flush=True)
     kt = {names[k]: g.kernel_time(k) for k in range(6)}
     import hashlib
     print("iter %d: %.4fs  %.1f plans/s  cov mean %.4f  fitness sha1 %s  counters %s" % (
