@@ -48,6 +48,7 @@ struct TileGeom {
     float Xl, Yl;        // this lane's pixel in block (0, 0); block (bx, by) adds (bx kx8, by ky4)
     float tXmin, tXmax, tYmin, tYmax;  // extreme pixel centres of the tile
     float bXmin, bXmax, bYmin, bYmax;  // extreme pixel centres of block b = lane
+    int sox = 0, soy = 0;              // the tile's first pixel inside its 128x128 supertile (binned variant)
 };
 
 // The same expression is used for a pixel whatever triangle is tested, so shared edges stay watertight; the tile and block
@@ -109,6 +110,7 @@ __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Sn
                                                  const SuperGeom* super = nullptr, unsigned* tilesOut = nullptr) {
     const float4 a = __ldg(sc.ta + tri), b = __ldg(sc.tb + tri), cc = __ldg(sc.tc + tri);
     float valid = -1.f;
+    unsigned boxWord = 0u;  // kPoseOnly: screen box of the triangle in pixels of the supertile
     if (b.w == 0.f) {  // not degenerate
         const double fX = sp->f[0], fY = sp->f[1], fZ = sp->f[2];
         const double ax = (double)a.x - (double)ox, ay = (double)a.y - (double)oy, az = (double)a.z - (double)oz;
@@ -141,6 +143,7 @@ __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Sn
             if constexpr (kPoseOnly) {
                 o[14] = zlo;
                 unsigned tiles = 0xffffu;
+                boxWord = 127u << 7 | 127u << 21;  // a vertex is not in front of the eye: the whole supertile
                 if (zlo > 1e-4f) {
                     const float ra = rcp_approx(za), rb = rcp_approx(zb), rc = rcp_approx(zc);
                     const float Xa = (float)ddot(ax, ay, az, sX, sY, sZ) * ra, Xb = (float)ddot(bx_, by_, bz_, sX, sY, sZ) * rb,
@@ -157,6 +160,11 @@ __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Sn
                     tiles = 0u;
                     if (c0 <= c1 && r0 <= r1)
                         tiles = (((2u << c1) - (1u << c0)) * 0x1111u) & ((16u << (4 * r1)) - 1u) & ~((1u << (4 * r0)) - 1u);
+                    // the pixel columns and rows of the supertile with a centre inside that box (7 bits each): stage_record() turns
+                    // them into the 8x4 blocks of a tile the triangle can touch
+                    const int px0 = min(127, max(0, (int)ceilf(fx0))), px1 = min(127, max(0, (int)floorf(fx1)));
+                    const int py0 = min(127, max(0, (int)ceilf(fy0))), py1 = min(127, max(0, (int)floorf(fy1)));
+                    boxWord = (unsigned)px0 | ((unsigned)px1 << 7) | ((unsigned)py0 << 14) | ((unsigned)py1 << 21);
                 }
 #if IPP_EXACT_TILE_MASK
                 if (super->tX && tiles != 0u) {
@@ -194,7 +202,10 @@ __device__ __forceinline__ bool setup_triangle_t(const DeviceScene& sc, const Sn
             }
         }
     }
-    o[15] = valid;
+    // a record keeps the screen box where the staged triangle keeps `valid` (stage_record() derives that from [14] again); its sign
+    // bit says whether the triangle survived
+    if constexpr (kPoseOnly) o[15] = valid >= 0.f ? __uint_as_float(boxWord) : -1.f;
+    else o[15] = valid;
     return valid >= 0.f;
 }
 __device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snapshot* sp, int tri, float* __restrict__ o, float ox,
@@ -207,17 +218,31 @@ __device__ __forceinline__ bool setup_triangle(const DeviceScene& sc, const Snap
 // bits as setup_triangle().  r was written by this warp earlier in the same kernel: plain loads.
 __device__ __forceinline__ bool stage_record(const float4* r, float* __restrict__ o, float zcull, const TileGeom& g) {
     const float4 q0 = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
-    float valid = q3.w;
+    float valid = __float_as_int(q3.w) >= 0 ? fmaxf(q3.z, 0.f) * 0.999999f : -1.f;  // as setup_triangle_t computes it
+    unsigned blocks = 0u;
     if (valid >= 0.f && q3.z <= zcull * 1.000001f) {
         const float ma = __fmaf_rn(q0.y, q0.y >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(q0.z, q0.z >= 0.f ? g.tYmax : g.tYmin, q0.x));
         const float mb = __fmaf_rn(q1.x, q1.x >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(q1.y, q1.y >= 0.f ? g.tYmax : g.tYmin, q0.w));
         const float mc = __fmaf_rn(q1.w, q1.w >= 0.f ? g.tXmax : g.tXmin, __fmaf_rn(q2.x, q2.x >= 0.f ? g.tYmax : g.tYmin, q1.z));
         if (fminf(fminf(ma, mb), mc) < 0.f) valid = -1.f;
+        // the 8x4 blocks of this tile (bit = row * 4 + column) that hold a pixel of the triangle's screen box: the three edge
+        // functions alone also accept blocks beyond a small triangle's corners (and, for a sliver whose coefficients are all
+        // rounding noise, pixels that are nowhere near it)
+        const unsigned w = __float_as_uint(q3.w);
+        const int x0 = (int)(w & 127u) - g.sox, x1 = (int)((w >> 7) & 127u) - g.sox;
+        const int y0 = (int)((w >> 14) & 127u) - g.soy, y1 = (int)((w >> 21) & 127u) - g.soy;
+        if (x1 >= 0 && y1 >= 0 && x0 < kTile && y0 < kTile) {
+            const int bx0 = max(x0, 0) >> 3, bx1 = min(x1, kTile - 1) >> 3, by0 = max(y0, 0) >> 2, by1 = min(y1, kTile - 1) >> 2;
+            const unsigned cols = (2u << bx1) - (1u << bx0);  // 4 bits
+            const unsigned rows = (by1 >= 7 ? 0xffffffffu : ((16u << (4 * by1)) - 1u)) & ~((1u << (4 * by0)) - 1u);
+            blocks = (cols * 0x11111111u) & rows;
+        }
+        if (blocks == 0u) valid = -1.f;
     } else {
         valid = -1.f;
     }
     float4* o4 = reinterpret_cast<float4*>(o);
-    o4[0] = q0; o4[1] = q1; o4[2] = q2; o4[3] = make_float4(q3.x, q3.y, q3.z, valid);
+    o4[0] = q0; o4[1] = q1; o4[2] = q2; o4[3] = make_float4(q3.x, q3.y, __uint_as_float(blocks), valid);
     return valid >= 0.f;
 }
 
@@ -226,6 +251,7 @@ __device__ __forceinline__ bool stage_record(const float4* r, float* __restrict_
 // depth against the block's farthest hit bz): one ballot gives the blocks that can still matter; the warp then runs the
 // ray/triangle test on those, every lane owning the same 32 pixels of the tile throughout.  Edge functions are monotone in X and Y
 // as computed (explicit fmaf), so the block rejection is exact.  Returns true when some hit changed.
+template <bool kBlockMask = false>
 __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__restrict__ tri)[kTriWords], float* __restrict__ St,
                                               int* __restrict__ Sid, const TileGeom& g, int lane, float zNear, float zFar, float zcull,
                                               float bz, unsigned* diagBlocks = nullptr) {
@@ -249,6 +275,7 @@ __device__ __forceinline__ bool raster_staged(unsigned live, const float (*__res
                            2e-6f * (fabsf(gs) + fabsf(gu) + fabsf(gf));
         const float zloBlk = fmaxf(zloTri, vol * rcp_approx(dmax) * 0.9999f);
         unsigned todo = __ballot_sync(0xffffffffu, fminf(fminf(ca, cb), cc) >= 0.f && dmax > 0.f && zloBlk <= bz);
+        if constexpr (kBlockMask) todo &= __float_as_uint(tr[14]);  // blocks inside the triangle's screen box (stage_record)
         if (diagBlocks) *diagBlocks += __popc(todo);
         // kBlocksPerStep blocks per step: their tests are independent (different pixels), which hides the latency of one behind
         // the others

@@ -36,6 +36,7 @@ constexpr int kBinWarps = 4;
 constexpr int kBinThreads = kBinWarps * 32;
 constexpr unsigned long long kNoEntry = ~0ull;
 constexpr int kSortRadixBits = 6;  // 12 depth bits = 2 passes
+constexpr int kSmallItems = 2;     // keys per thread of the short sort a pose with few surviving leaves takes
 constexpr int kBinRecords = 4096;   // set-up triangles (64 B each) a warp can keep for one supertile (or part of one)
 #ifndef IPP_STAGE_MIN
 #define IPP_STAGE_MIN 1
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
     unsigned long long* stage = reinterpret_cast<unsigned long long*>(smemRaw);  // keys before the sort (same bytes as temp)
     __shared__ unsigned rowMask[32];
     __shared__ int nValid;
+    __shared__ int warpTotal[32];
     __shared__ unsigned superHalf[2];
 
     const int si = blockIdx.x, tid = threadIdx.x;
@@ -183,15 +185,50 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) k_leaf_tabl
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) keys[it] = stage[it * THREADS + tid];
     __syncthreads();
-    Sort(temp).Sort(keys, 52, 64);  // stable: entries of equal depth keep their (fixed) input order
-    __syncthreads();
     unsigned long long* out = table + (size_t)si * stride;
     const int n = nValid;
+    if (ITEMS > kSmallItems && n <= THREADS * kSmallItems) {
+        // A pose keeps a fraction of the leaves (a tenth on the bench workload): the surviving keys are compacted, in the order
+        // the full sort takes its input in (thread, item), and a sort of kSmallItems keys per thread finishes the job -- same
+        // keys, same relative order of equal depths, same table.
+        int cnt = 0;
 #pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const int pos = tid * ITEMS + it;
-        if (pos < n) out[pos] = keys[it];
+        for (int it = 0; it < ITEMS; ++it) cnt += keys[it] != kNoEntry ? 1 : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += v;
+        }
+        if ((tid & 31) == 31) warpTotal[tid >> 5] = incl;
+        __syncthreads();
+        int base = incl - cnt;
+        for (int w = 0; w < (tid >> 5); ++w) base += warpTotal[w];
+        unsigned long long* compact = stage;  // the keys are in registers: the staging area is free
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it)
+            if (keys[it] != kNoEntry) compact[base++] = keys[it];
+        __syncthreads();
+        using SortS = cub::BlockRadixSort<unsigned long long, THREADS, kSmallItems, cub::NullType, kSortRadixBits>;
+        unsigned long long ks[kSmallItems];
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) ks[j] = tid * kSmallItems + j < n ? compact[tid * kSmallItems + j] : kNoEntry;
+        __syncthreads();
+        SortS(*reinterpret_cast<typename SortS::TempStorage*>(smemRaw)).Sort(ks, 52, 64);
+#pragma unroll
+        for (int j = 0; j < kSmallItems; ++j) {
+            const int pos = tid * kSmallItems + j;
+            if (pos < n) out[pos] = ks[j];
+        }
+    } else {
+        Sort(temp).Sort(keys, 52, 64);  // stable: entries of equal depth keep their (fixed) input order
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const int pos = tid * ITEMS + it;
+            if (pos < n) out[pos] = keys[it];
+        }
     }
+    __syncthreads();
     if (tid < 64) {
         const int ssx = tid & 7, ssy = tid >> 3;
         const unsigned any = (rowMask[4 * ssy] | rowMask[4 * ssy + 1] | rowMask[4 * ssy + 2] | rowMask[4 * ssy + 3]) & (0xFu << (4 * ssx));
@@ -440,6 +477,8 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                     }
                     TileGeom tg;
                     tile_geometry(tg, tpx0, tpy0, lane, kx, cx, ky, cy);
+                    tg.sox = (tl & 3) * kTile;
+                    tg.soy = (tl >> 2) * kTile;
                     // zcull: nothing beyond this depth can matter to any ray of the tile; lane b keeps the same for 8x4 block b in bzReg
                     // (0: block outside the image)
                     float zcull = zFarCull, bzReg = ((lane & 3) * 8 < vw && (lane >> 2) * 4 < vh) ? zFarCull : 0.f;
@@ -473,10 +512,10 @@ __global__ void __launch_bounds__(kBinThreads, 5) k_visibility_bins(DeviceScene 
                                 if (sub == 0u) continue;
 #ifdef IPP_VIS_DIAG
                                 unsigned nb = 0;
-                                const bool dirty = raster_staged(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg, &nb);
+                                const bool dirty = raster_staged<true>(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg, &nb);
                                 dBlocks += nb;
 #else
-                                const bool dirty = raster_staged(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
+                                const bool dirty = raster_staged<true>(sub, S.tri, S.t, S.id, tg, lane, zNear, zFar, zcull, bzReg);
 #endif
                                 if (__any_sync(0xffffffffu, dirty)) {
                                     tileHit = true;
