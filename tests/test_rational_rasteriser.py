@@ -200,12 +200,11 @@ def test_oracle_item_buffer_equals_the_exact_rational_rule(oracle_mod, tmp_path,
 
 
 def test_the_two_depth_models_differ_only_where_they_should(oracle_mod, tmp_path):
-    """Coplanar duplicates: model 0 gives every pixel to the lower id (tie band), model 1 too (GL_LESS keeps the first drawn).  Two
-    parallel sheets 1e-5 apart at 6 m: inside model 0's relative 2^-16 band (the lower id wins although it is behind), while a 24-bit
-    window depth at 6 m resolves 1e-5 ... does not: one step of 2^-24 of window depth at z = 6 m, n = 0.1, f = 10 is
-    z^2 (f - n) / (f n) 2^-24 = 2.1e-6 m, so GL_LESS keeps the nearer sheet.  The exact rule says the same for both."""
+    """Two parallel sheets 60 um apart at 6 m, the farther one with the lower id.  Model 0: 60 um is inside the relative 2^-16 tie
+    band (92 um at 6 m), so the lower id wins although it is behind.  Model 1: one step of a 24-bit window depth at z = 6 m, n = 0.1,
+    f = 10 is z^2 (f - n) / (f n) 2^-24 = 21 um, so GL_LESS keeps the nearer sheet.  The exact rule says the same for both."""
     near_sheet = [[-3.0, 6.0, -3.0], [3.0, 6.0, -3.0], [0.0, 6.0, 3.0]]
-    far_sheet = [[-3.0, 6.00001, -3.0], [3.0, 6.00001, -3.0], [0.0, 6.00001, 3.0]]
+    far_sheet = [[-3.0, 6.00006, -3.0], [3.0, 6.00006, -3.0], [0.0, 6.00006, 3.0]]
     tris = np.asarray([far_sheet, near_sheet], dtype=np.float32)  # id 0 is the farther one
     assert float(tris[0, 0, 1]) > float(tris[1, 0, 1])
     for model, owner in ((0, 0), (1, 1)):

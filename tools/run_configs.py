@@ -1,6 +1,7 @@
 """BASELINE.json configs other than the bench workload, on the CUDA evaluator (timings only; parity is in tests/).
 
     python tools/run_configs.py c1        cube 12 288 triangles, NSGA-II pop 100 x 20 generations (optimize_coverage.py flow)
+    python tools/run_configs.py c1cpu     the same run with the CPU oracle as the evaluator (the reference-side leg of config 1)
     python tools/run_configs.py c3 [pop]  luis4.obj (stand-in for oil_manifold.stl), pop x 30-viewpoint plans, cold + warm
     python tools/run_configs.py c4 [pop]  luis1..5 one after the other (multiRun.py style), pop plans of 2..15 viewpoints each, setup included
     python tools/run_configs.py c5 [lvl]  displaced icosphere (20 * 4^lvl triangles), 1 000 x 50-viewpoint plans (BVH-walk variant above 16 384 leaves)
@@ -66,6 +67,26 @@ def c1():
         g.close()
 
 
+def c1cpu():
+    """config 1 as the reference ran it: the same seeded NSGA-II loop with the CPU restatement of the reference evaluator (oracle/,
+    one thread, like the reference's serial toolbox.map) -- the CPU leg beside c1"""
+    from oracle import oracle as om
+    om.build()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "cube.ippm")
+        synth_meshes.write_ippm(path, synth_meshes.cube())
+        params = oc.Parameters(NUM_INDIVS=100, NUM_GENERATIONS=20)
+        t = time.perf_counter()
+        o = om.Oracle(path, params.SENSOR_PARAMETERS)
+        setup = time.perf_counter() - t
+        pop, pf, logbook, stats = oc.run_nsga2(o, params, seed=20261019)
+        print(json.dumps({"config": "c1 cube 12288 triangles, NSGA-II pop 100 x 20 generations, CPU restatement of the reference evaluator, 1 thread",
+                          "setup_s": setup, "total_s": stats["total_s"], "evaluator_s": stats["eval_s"], "evaluations": stats["evaluations"],
+                          "batched_calls": stats["calls"], "pareto_front": len(pf),
+                          "hypervolume": oc.hypervolume_2d([i.fitness for i in pf], params.HYPERVOLUME_REF_POINT),
+                          "best_score": logbook[-1]["fit_min"][0], "memoised_edges": stats["memoised_edges"]}), flush=True)
+
+
 def c3(pop=2000):
     g = cpp_binding.PlanCoverageEstimator(os.path.join(MESHES, "luis4.ippm"), SPECS)
     ids, off = population(np.random.default_rng(20261019), g.getNumberOfBoxes(), pop, 30, 30)
@@ -100,4 +121,4 @@ def c5(level=6, pop=200):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c1"
     arg = [int(x) for x in sys.argv[2:]]
-    {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[which](*arg)
+    {"c1": c1, "c1cpu": c1cpu, "c3": c3, "c4": c4, "c5": c5}[which](*arg)
