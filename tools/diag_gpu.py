@@ -16,8 +16,14 @@ H = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 pop = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 V = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 
+path = mesh_path(mesh)
+if mesh.startswith("ico"):  # the displaced icosphere of BASELINE config 5 (ico8: 1 310 720 triangles)
+    import tempfile
+    from inspection_path_planning_b200 import synth_meshes
+    path = os.path.join(tempfile.mkdtemp(), mesh + ".ippm")
+    synth_meshes.write_ippm(path, synth_meshes.icosphere(level=int(mesh[3:])))
 t = time.time()
-g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), specs(H))
+g = cpp_binding.PlanCoverageEstimator(path, specs(H))
 print("setup %.3fs T=%d N=%d maxE=%.6f" % (time.time() - t, g.T, g.getNumberOfBoxes(), g.getMaxAllowedEnergy()), flush=True)
 rng = np.random.default_rng(20261019)
 plans = cpp_binding.pack_population(random_plans(rng, g.getNumberOfBoxes(), pop, V))
