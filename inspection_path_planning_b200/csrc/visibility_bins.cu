@@ -1,22 +1,24 @@
 // visibility_bins.cu -- K4b: edge visibility with depth-sorted leaf bins instead of a BVH walk per tile.  Same item-buffer sampling
 // and the same per-tile rasteriser as visibility.cu (raster.cuh); what changes is how a tile finds its triangles.
 //
-//   k_leaf_table  one CTA per camera pose: every BVH leaf box (a few thousand for the reference's meshes) is projected -- 8 corners,
+//   k_leaf_table  one CTA per rendered camera pose: every cluster box (a BVH leaf, or a subtree of <= kMaxClusterTris triangles for
+//                 meshes with more than kMaxBinLeaves leaves; a few thousand for the reference's meshes) is projected -- 8 corners,
 //                 screen rectangle in 32x32-pixel tile units with a one-pixel margin, nearest depth -- culled against the view
-//                 volume, packed into one 64-bit word [depth:16 | tx0 tx1 ty0 ty1:20 | first triangle, count:28] and block-radix
-//                 sorted by depth (cub::BlockRadixSort, stable, so the order is deterministic).  The CTA also ORs the rectangles
-//                 into a 32x32 tile occupancy mask and an 8x8 supertile mask: empty tiles are never scheduled.
-//   k_visibility_bins  persistent grid, one warp per occupied 128x128 supertile: one coalesced pass over the pose's table keeps the
-//                 entries that touch the supertile (per-warp list in a scratch).  The tile-independent half of the triangle set-up
-//                 then runs once per triangle of that list: triangles that can produce a fragment in the supertile become 64-byte
-//                 records (a second per-warp scratch) and, for every tile of the supertile that the triangle's screen box touches,
-//                 one 4-byte entry [depth key of its cluster | record] in that tile's list (a third).  The warp then rasterises its
-//                 <= 16 tiles one after the other: a tile reads its own list front to back, 32 records per staging round, and
-//                 stops at the first entry behind its farthest hit -- strict front-to-back order makes the hierarchical depth
-//                 culling of raster.cuh bite much earlier than the approximate order of a BVH walk, no dependent node fetch is
-//                 left on the critical path, and a tile never looks at a triangle that cannot touch it.  A supertile with more
-//                 surviving triangles than the record scratch holds is split into halves (down to single tiles, which take their
-//                 triangles in several batches).
+//                 volume, packed into one 64-bit word [depth:16 | tx0 tx1 ty0 ty1:20 | cluster:28]; the survivors are compacted and
+//                 block-radix sorted by depth (cub::BlockRadixSort, stable, so the order is deterministic).  The CTA also ORs the
+//                 rectangles into a 32x32 tile occupancy mask and an 8x8 supertile mask: empty tiles are never scheduled.
+//   k_visibility_bins  persistent grid, one warp per occupied 128x128 supertile (or per quadrant / tile of one when a launch has
+//                 too few supertiles to fill the grid): one coalesced pass over the pose's table keeps the entries that touch the
+//                 supertile (per-warp list in a scratch).  The tile-independent half of the triangle set-up then runs once per
+//                 triangle of that list: triangles that can produce a fragment in the supertile become 64-byte records (a second
+//                 per-warp scratch) with a 4-byte header each [depth key of the cluster:16 | tiles of the supertile the triangle
+//                 can touch:16] -- the exact tile-level edge test, not the screen box.  The warp then rasterises its <= 16 tiles
+//                 one after the other: a tile scans the headers front to back, 32 per load, stages the records that carry its bit
+//                 as soon as a chunk has produced any (so that the depth bounds stay fresh), and stops at the first chunk behind
+//                 its farthest hit -- strict front-to-back order makes the hierarchical depth culling of raster.cuh bite much
+//                 earlier than the approximate order of a BVH walk, no dependent node fetch is left on the critical path, and a
+//                 tile never looks at a triangle that cannot touch it.  A supertile with more surviving triangles than the record
+//                 scratch holds is split into halves (down to single tiles, which take their triangles in several batches).
 //
 // Used when the mesh has <= kMaxBinLeaves clusters of <= kMaxClusterTris triangles (meshes up to ~2 M triangles) and the image is
 // <= 1024 pixels a side; other inputs take the BVH-walking kernel of visibility.cu.
