@@ -1,3 +1,4 @@
+# bench.py on N GPUs of one box under torch.distributed.run: bash tools/bench_n.sh <N>   (gpurun --gpus N)
 set -u
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"

@@ -1,4 +1,5 @@
-# round 2 evidence run: GPU tests, the bench line, the launch list of the bench command, --set full captures of K4 / leaf table / K6
+# The evidence run of a round on one B200 (under gpurun): GPU tests, the bench line, the reference arm, the launch list of the bench
+# command, --set full captures of K4 + cluster tables, config 1 on GPU and CPU.  Outputs go to gpurun_out/; profiles/README.md says which are kept.
 set -u
 timeout -s KILL 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2f_pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -3 gpurun_out/r2f_pytest_gpu.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err; echo "bench rc $?"
