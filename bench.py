@@ -404,7 +404,7 @@ def run_c3(args, L, comm, local, peaks):
     warm = {"ms_per_step": warm_s / C3_WARM_STEPS * 1e3, "plans_per_s": pop * C3_WARM_STEPS / warm_s, "same_rows_as_cold": same,
             "note": "wall clock around the host-pointer call: H2D of %d B of genes, probe kernel, K6 on this rank's shard, all-gather of "
                     "the fitness rows, D2H of %d B" % (ids.nbytes + offsets.nbytes, pop * 32)}
-    k6 = {"kernel": "k_plan_reduce (row-major streaming form)", "bound": "hbm", "plans_per_launch": shard, "us_per_launch": k6_s * 1e6,
+    k6 = {"kernel": "k_plan_reduce_rows_g<8, 4, 5> (row-major streaming form, areas from global memory)", "bound": "hbm", "plans_per_launch": shard, "us_per_launch": k6_s * 1e6,
           "bytes_per_plan": b_plan, "achieved": shard * b_plan / k6_s / 1e9 if k6_s > 0 else 0.0, "peak": hbm, "unit": "GB/s",
           "frac": (shard * b_plan / k6_s / 1e9 / hbm) if k6_s > 0 else 0.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
           "row_pool_gb": ev.memo_size() * ((words + 3) // 4 * 16) / 1e9,

@@ -482,6 +482,66 @@ __global__ void __launch_bounds__(PLANS * 32, MINB) k_plan_reduce_rows(PlanReduc
     }
 }
 
+// The row-major kernel with the areas read straight from global memory (L1 / L2 resident: T doubles) instead of bulk-copied area
+// tiles in shared memory: no barrier couples the warps of a CTA, so a warp that waits for a row does not hold the others back.
+template <int PLANS, int NB, int MINB>
+__global__ void __launch_bounds__(PLANS * 32, MINB) k_plan_reduce_rows_g(PlanReduceArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long rowWords = a.rowWords;
+    const int nSuper = (a.nTiles + NB - 1) / NB;
+    const int nb = (a.nTiles + nSuper - 1) / nSuper;
+    for (long long p = (long long)blockIdx.x * PLANS + warp; p < a.pop; p += (long long)gridDim.x * PLANS) {
+        if (!a.active[p]) continue;
+        const long long lo = a.offsets[p];
+        const int nGenes = (int)(a.offsets[p + 1] - lo);
+        const int mm = nGenes == 0 ? 0 : nGenes + (a.hasStart ? 1 : 0) + (a.loops ? 1 : 0);
+        const int nEdges = mm > 0 ? mm - 1 : 0;
+        auto boxAt = [&](int k) -> int {
+            if (a.hasStart) {
+                if (k == 0) return a.N;
+                k -= 1;
+            }
+            return k < nGenes ? a.ids[lo + k] : a.ids[lo];
+        };
+        auto rowOfEdge = [&](int e) -> int {
+            if (e >= nEdges) return -1;
+            return a.rowmap[boxAt(e) * a.N + boxAt(e + 1)];
+        };
+        AreaAcc acc;
+        acc.clear();
+        for (int sup = 0; sup < nSuper; ++sup) {
+            uint4 m[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) m[u] = make_uint4(0, 0, 0, 0);
+            const long long w0 = (long long)sup * nb * kTileWords + lane * 4;
+            for (int e0 = 0; e0 < nEdges; e0 += 32) {
+                const int myRow = rowOfEdge(e0 + lane);
+                const int cnt = min(32, nEdges - e0);
+                for (int e = 0; e < cnt; ++e) {
+                    const int r = __shfl_sync(0xffffffffu, myRow, e);
+                    if (r < 0) continue;
+                    const uint32_t* row = a.rows + (size_t)r * rowWords + w0;
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        if (u < nb && w0 + u * kTileWords < rowWords) {
+                            const uint4 v = ldg_stream((const uint4*)(row + u * kTileWords));
+                            m[u].x |= v.x; m[u].y |= v.y; m[u].z |= v.z; m[u].w |= v.w;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int tile = sup * nb + u;
+                if (u >= nb || tile >= a.nTiles) break;
+                add_tile_area(acc, m[u], a.area + (size_t)tile * kTileTris, lane);
+            }
+        }
+        const double covered = combine_area(acc);
+        if (lane == 0) a.fitness[4 * p] = 1.0 - (covered / a.totalArea);
+    }
+}
+
 // The same reduce with two options.  kRows: rows come from the explicit per-edge list ([id, angle] genes, heading search) instead
 // of rowmap[key]; kSplit: the tiles of a plan are spread over gridDim.y CTAs in blocks of kBlockTiles (small populations on large
 // meshes), per-block area sums go to a.partial and k_plan_finish adds them up in block order.
@@ -725,6 +785,12 @@ void launch_rows(const PlanReduceArgs& a, int numSMs, cudaStream_t st) {
     const int grid = (int)std::min<long long>((long long)numSMs * MINB, groups);
     k_plan_reduce_rows<PLANS, NB, EU, MINB><<<grid, PLANS * 32, smem, st>>>(a);
 }
+template <int PLANS, int NB, int MINB>
+void launch_rows_g(const PlanReduceArgs& a, int numSMs, cudaStream_t st) {
+    const long long groups = (a.pop + PLANS - 1) / PLANS;
+    const int grid = (int)std::min<long long>((long long)numSMs * MINB, groups);
+    k_plan_reduce_rows_g<PLANS, NB, MINB><<<grid, PLANS * 32, 0, st>>>(a);
+}
 }  // namespace
 
 const char* plan_reduce_variant_name(int v) {
@@ -742,6 +808,16 @@ const char* plan_reduce_variant_name(int v) {
         case 10: return "ldg row-major PLANS=16 NB=9 EU=1, 1 CTA/SM";
         case 11: return "ldg row-major PLANS=8 NB=4 EU=2, 3 CTA/SM";
         case 12: return "ldg row-major PLANS=12 NB=4 EU=1, 3 CTA/SM";
+        case 13: return "ldg row-major, areas from global, PLANS=12 NB=4, 3 CTA/SM";
+        case 14: return "ldg row-major, areas from global, PLANS=8 NB=4, 5 CTA/SM";
+        case 15: return "ldg row-major, areas from global, PLANS=8 NB=4, 6 CTA/SM";
+        case 16: return "ldg row-major, areas from global, PLANS=8 NB=8, 4 CTA/SM";
+        case 17: return "ldg row-major, areas from global, PLANS=4 NB=4, 10 CTA/SM";
+        case 18: return "ldg row-major, areas from global, PLANS=8 NB=4, 4 CTA/SM";
+        case 19: return "ldg row-major, areas from global, PLANS=10 NB=4, 4 CTA/SM";
+        case 20: return "ldg row-major, areas from global, PLANS=8 NB=2, 5 CTA/SM";
+        case 21: return "ldg row-major, areas from global, PLANS=16 NB=4, 2 CTA/SM";
+        case 22: return "ldg row-major, areas from global, PLANS=8 NB=3, 5 CTA/SM";
         default: return "auto";
     }
 }
@@ -762,6 +838,16 @@ void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st) {
             case 10: launch_rows<16, 9, 1, 1>(a, numSMs, st); return;
             case 11: launch_rows<8, 4, 2, 3>(a, numSMs, st); return;
             case 12: launch_rows<12, 4, 1, 3>(a, numSMs, st); return;
+            case 13: launch_rows_g<12, 4, 3>(a, numSMs, st); return;
+            case 14: launch_rows_g<8, 4, 5>(a, numSMs, st); return;
+            case 15: launch_rows_g<8, 4, 6>(a, numSMs, st); return;
+            case 16: launch_rows_g<8, 8, 4>(a, numSMs, st); return;
+            case 17: launch_rows_g<4, 4, 10>(a, numSMs, st); return;
+            case 18: launch_rows_g<8, 4, 4>(a, numSMs, st); return;
+            case 19: launch_rows_g<10, 4, 4>(a, numSMs, st); return;
+            case 20: launch_rows_g<8, 2, 5>(a, numSMs, st); return;
+            case 21: launch_rows_g<16, 4, 2>(a, numSMs, st); return;
+            case 22: launch_rows_g<8, 3, 5>(a, numSMs, st); return;
             default: break;
         }
     }
@@ -778,10 +864,16 @@ void launch_plan_reduce(const PlanReduceArgs& a, int numSMs, cudaStream_t st) {
     } else if (rows) {
         launch_plan_reduce_t<true, false>(a, numSMs, 1, st);
     } else if (a.pop >= (long long)numSMs * 3 * kPlansPerCtaWide) {
-        // enough plans for three CTAs of 12 warps on every SM (36 warps per SM instead of 24 keep more row reads in flight): the
-        // row-major kernel, 2 KB contiguous per row and step.  Measured at 100 000 plans, L2 flushed (profiles/r2_k6_variants.md):
-        // luis4 73.7 % of the HBM copy peak against 67.0 % for the tile-major kernel, mockup_only 66.6 % against 62.2 %.
-        launch_rows<12, 4, 1, 3>(a, numSMs, st);
+        // enough plans to fill the machine with 40 warps per SM: the row-major kernel that reads the areas from global memory (no
+        // shared-memory area tiles, so no barrier couples the warps of a CTA and five CTAs of 8 plans fit an SM).  Measured at
+        // 100 000 plans, L2 flushed (profiles/r2_k6_variants.md): luis4 96 % of the HBM copy peak against 72.7 % for the row-major
+        // kernel with staged area tiles and 67 % for the tile-major kernel; mockup_only 68 % against 62.5 %.  Below a full wave
+        // (3 000 plans on luis4, 1 000 on mockup_only) the tile-major kernel is 10-20 % faster and keeps those populations.
+        // Every plan then reads the whole area array through L1 / L2 (8 T bytes, about as much as its rows): fine up to the 327 680
+        // triangles of ico7 (80 tiles: 114 % against 89 %), a loss on the 1.3 M triangles of config 5 (320 tiles: 72 % against
+        // 85 %), where the kernel that stages each area tile once per CTA keeps the job.
+        if (a.nTiles <= 128) launch_rows_g<8, 4, 5>(a, numSMs, st);
+        else launch_rows<12, 4, 1, 3>(a, numSMs, st);
     } else {
         launch_stream<kPlansPerCta>(a, numSMs, st);
     }

@@ -15,7 +15,13 @@ pops = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1000,
 V = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 nedges = int(sys.argv[5]) if len(sys.argv) > 5 else 20000
 variants = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0]
-g = cpp_binding.PlanCoverageEstimator(mesh_path(mesh), specs(H))
+path = mesh_path(mesh)
+if mesh.startswith("ico"):  # the displaced icosphere of BASELINE config 5 (ico8: 1 310 720 triangles)
+    import tempfile
+    from inspection_path_planning_b200 import synth_meshes
+    path = os.path.join(tempfile.mkdtemp(), mesh + ".ippm")
+    synth_meshes.write_ippm(path, synth_meshes.icosphere(level=int(mesh[3:])))
+g = cpp_binding.PlanCoverageEstimator(path, specs(H))
 L = _lib.load()
 N = g.getNumberOfBoxes(); T = g.T
 rng = np.random.default_rng(1)
