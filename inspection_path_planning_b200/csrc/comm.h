@@ -19,5 +19,5 @@ void comm_eval_and_allgather(Evaluator& ev, const int32_t* ids, const float* ang
 // device-resident form: this rank's `mine` plans (d_ids / d_offsets on the device) are evaluated into slot `rank` of
 // d_gather (world * per rows of 4 doubles) and the slots are all-gathered in place; asynchronous on the evaluator's stream
 void comm_eval_device_and_allgather(Evaluator& ev, const int32_t* d_ids, const float* d_angles, const int64_t* d_offsets, int64_t mine,
-                                    int64_t nGenes, int64_t per, bool memo, bool noLimit, double* d_gather);
+                                    int64_t nGenes, int64_t per, bool memo, bool noLimit, double* d_gather, bool shardBad = false);
 }  // namespace ipp
