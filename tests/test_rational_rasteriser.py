@@ -166,6 +166,26 @@ def _scene(seed, n_tris):
     return np.asarray(tris, dtype=np.float32)
 
 
+def _sheet(seed, n=7):
+    """a bumpy n x n vertex sheet in front of the camera, two triangles per cell, every interior edge shared by exactly two triangles
+    (watertightness: no pixel inside the outline may show the backdrop triangle behind it), plus that backdrop"""
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(-1.3, 1.3, n)[:, None] + rng.uniform(-0.12, 0.12, size=(n, n))
+    zs = np.linspace(-1.3, 1.3, n)[None, :] + rng.uniform(-0.12, 0.12, size=(n, n))
+    ys = 3.0 + rng.uniform(-0.4, 0.4, size=(n, n))
+    v = np.stack([xs, ys, zs], axis=2)
+    tris = []
+    for i in range(n - 1):
+        for j in range(n - 1):
+            a, b, c, d = v[i, j], v[i + 1, j], v[i + 1, j + 1], v[i, j + 1]
+            if (i + j) % 2:
+                tris += [[a, b, c], [a, c, d]]
+            else:
+                tris += [[a, b, d], [b, c, d]]
+    tris.append([[-6.0, 8.0, -6.0], [6.0, 8.0, -6.0], [0.0, 8.0, 7.0]])  # the backdrop: id 2 (n-1)^2
+    return np.asarray(tris, dtype=np.float32)
+
+
 CAMERAS = {
     # f, s = f x up / |.|, u = s x f with up = (0, 0, 1): all components exactly representable
     "along_y": ((0.0, 0.0, 0.0), ((0, 1, 0), (1, 0, 0), (0, 0, 1))),
@@ -197,6 +217,20 @@ def test_oracle_item_buffer_equals_the_exact_rational_rule(oracle_mod, tmp_path,
     assert (want >= 0).mean() > 0.3  # the scene fills a good part of the image
     assert len(np.unique(want[want >= 0])) >= 6
     assert np.array_equal(got[robust], want[robust]), np.argwhere((got != want) & robust)[:10]
+
+
+def test_shared_edges_are_watertight(oracle_mod, tmp_path):
+    """A sheet of 72 triangles whose interior edges are each shared by two of them, in front of a backdrop: by the exact rule every
+    pixel whose ray passes inside the sheet's outline shows a sheet triangle; the oracle must agree pixel for pixel (a crack between
+    two triangles would show the backdrop's id)."""
+    tris = _sheet(11)
+    backdrop = len(tris) - 1
+    want, robust = rational_item_buffer(tris, (0, 0, 0), CAMERAS["along_y"][1], 24, 24, 46, 0.1, 10.0, 0)
+    got = _oracle_ids(oracle_mod, tmp_path, tris, "along_y", 24, 0)
+    assert robust.mean() > 0.97 and (want != backdrop).mean() > 0.5
+    assert np.array_equal(got[robust], want[robust])
+    inner = want[6:18, 6:18]
+    assert (inner != backdrop).all() and (inner >= 0).all()  # the middle of the image is all sheet
 
 
 def test_the_two_depth_models_differ_only_where_they_should(oracle_mod, tmp_path):
@@ -233,13 +267,13 @@ def test_top_left_rule_on_a_shared_edge_through_pixel_centres(oracle_mod, tmp_pa
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cam,seed,px", [("along_y", 1, 24), ("along_minus_x", 3, 32)])
+@pytest.mark.parametrize("cam,seed,px", [("along_y", 1, 24), ("along_minus_x", 3, 32), ("along_y", -11, 32)])
 def test_gpu_item_buffer_equals_the_exact_rational_rule(oracle_mod, tmp_path, cam, seed, px):
     """libipp.so's id image (the test hook of K4: the same rasteriser the edge bitmaps come from) against the exact rule.  The
     kernel rounds its 13 coefficients to float32, so a centre may be decided differently within ~1e-6 of an edge: pixels are
     compared where the exact rule is robust to 1e-5 of the triangle size, and at most 1 % of them may be excluded."""
     from inspection_path_planning_b200 import cpp_binding
-    tris = _scene(seed, 14)
+    tris = _scene(seed, 14) if seed >= 0 else _sheet(-seed)  # negative seed: the watertight sheet (shared edges, float coefficients)
     if cam == "along_minus_x":
         tris = np.stack([-tris[:, :, 1] + 0.5, tris[:, :, 0] + 1.0, tris[:, :, 2] + 0.25], axis=2).astype(np.float32)
     eye, basis = CAMERAS[cam]
