@@ -731,8 +731,8 @@ def run_gpu(args):
         "plan_reduce_config2_warm": warm,
         "c3": c3,
     }
-    # CPU baseline beside it: the CPU restatement on this box's host cores, bounded samples
-    if not args.no_cpu_baseline:
+    # CPU baseline beside it: the CPU restatement on this box's host cores, bounded samples (rank 0 at N = 1 only)
+    if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_legs(n_boxes, host_cores())
     print(json.dumps(line))
     return 0
